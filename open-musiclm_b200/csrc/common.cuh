@@ -1,0 +1,75 @@
+// Shared host/device helpers for libomlm_b200: error plumbing, TMA descriptor cache, small math.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace omlm {
+
+// ---- error reporting across the C ABI (no exceptions cross the boundary) -----------------
+void set_last_error(const char* fmt, ...);
+#define OMLM_CHECK_ARG(cond, ...)          \
+  do {                                     \
+    if (!(cond)) {                         \
+      ::omlm::set_last_error(__VA_ARGS__); \
+      return 1;                            \
+    }                                      \
+  } while (0)
+#define OMLM_CUDA(expr)                                                                       \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      ::omlm::set_last_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return 1000 + static_cast<int>(_e);                                                     \
+    }                                                                                         \
+  } while (0)
+#define OMLM_LAUNCH_CHECK() OMLM_CUDA(cudaGetLastError())
+
+// ---- TMA descriptors ----------------------------------------------------------------------
+// 2-D bf16 tensor map: inner (contiguous) extent dim0, outer extent dim1, row pitch in bytes,
+// box {box0, box1}, SWIZZLE_128B (box0 * 2 bytes must be 128).
+int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t dim0, uint64_t dim1,
+                      uint64_t pitch_bytes, uint32_t box0, uint32_t box1);
+
+int num_sms();
+
+// ---- device math --------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
+  __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&v);
+  return __bfloat1622float2(t);
+}
+__device__ __forceinline__ float bf16_round(float x) {
+  return __bfloat162float(__float2bfloat16_rn(x));
+}
+
+// Philox-4x32-10 counter RNG (dropout / forgetful-mask randomness; replayable in backward).
+__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                            uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+}  // namespace omlm

@@ -1,0 +1,328 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  C[m,n] = alpha * sum_k A(m,k) * B(n,k) (+ addend)
+//
+//   warp 0      : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1      : tcgen05.mma issuer (one elected lane), accumulators in TMEM, double-buffered
+//   warps 2..5  : epilogue (tcgen05.ld TMEM -> registers -> fused epilogue -> global)
+//
+// Operand majors are template parameters so that one kernel serves the forward projections
+// (A K-major, B K-major: nn.Linear weights are [out,in]), the data-gradient GEMMs (B MN-major: the
+// same weight read "transposed" without a transposed copy) and the weight-gradient GEMMs
+// (A and B MN-major: activations [tokens, features] contracted over tokens).
+//
+// This replaces the cuBLAS calls behind nn.Linear / einsum in the reference
+// (open_musiclm/transformer.py:144,149,254,333; open_musiclm/open_musiclm.py:173,181).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "../../include/omlm_b200.h"
+
+namespace omlm {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int kGemmThreads = 192;
+constexpr int kSmemBudget = 196608;  // ring bytes
+
+struct EpiParams {
+  void* out;            // bf16 or fp32
+  const float* addend;  // optional fp32 [M, ldadd]
+  long ldo;
+  long ldadd;
+  float alpha;
+  int out_f32;    // 0: bf16, 1: fp32
+  int atomic;     // 1: red.add into fp32 out (split-K)
+  int vec_ok;     // 16-byte vector stores allowed
+  int row_split;  // >0: rows are two halves of row_split, each with row_valid live rows
+  int row_valid;
+  int n_valid;    // columns >= n_valid are dropped
+};
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = kSmemBudget / kStageBytes;
+};
+
+template <int BN, int A_MN, int B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const EpiParams ep, const int M, const int N, const int K, const int splits) {
+  using S = GemmSmem<BN>;
+  constexpr int kStages = S::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024B alignment is required by the 128B swizzle atoms.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (M + BM - 1) / BM;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int kb_total = (K + BK - 1) / BK;
+  const int kb_per_split = (kb_total + splits - 1) / splits;
+  const int work_total = m_tiles * n_tiles * splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < kStages; ++i) {
+        mbar_init(&full_bar[i], 1);
+        mbar_init(&empty_bar[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&tfull_bar[i], 1);
+        mbar_init(&tempty_bar[i], 4);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
+        const int split = w % splits;
+        const int tile = w / splits;
+        const int n_blk = tile % n_tiles, m_blk = tile / n_tiles;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb_total, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::kStageBytes;
+          uint8_t* sb = sa + S::kABytes;
+          mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+          if (A_MN == 0) {
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c)
+              tma_load_2d(sa + c * 8192, &tmA, &full_bar[stage], m_blk * BM + c * 64, kb * BK);
+          }
+          if (B_MN == 0) {
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_2d(sb + c * 8192, &tmB, &full_bar[stage], n_blk * BN + c * 64, kb * BK);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
+        const int split = w % splits;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb_total, kb0 + kb_per_split);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+          const uint32_t sb = sa + S::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major: 16 elements = 32 bytes inside the swizzle row; 8-row groups 1024B apart.
+            // MN-major: 16 k-rows = 2048 bytes; 64-element MN chunks 8192B apart (LBO), 8-row groups 1024B (SBO).
+            const uint64_t ad = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024)
+                                     : make_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t bd = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024)
+                                     : make_smem_desc(sb + k * 32, 16, 1024);
+            umma_bf16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
+      const int tile = w / splits;
+      const int n_blk = tile % n_tiles, m_blk = tile / n_tiles;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      int row = m_blk * BM + quarter * 32 + lane;
+      bool row_ok = row < M;
+      if (ep.row_split > 0) {
+        const int half = row / ep.row_split, r = row - half * ep.row_split;
+        row_ok = row_ok && r < ep.row_valid;
+        row = half * ep.row_valid + r;
+      }
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = n_blk * BN + c * 32;
+        if (row_ok && col0 < ep.n_valid) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
+          const bool full = (col0 + 32 <= ep.n_valid) && ep.vec_ok;
+          if (ep.addend != nullptr) {
+            const float* ap = ep.addend + static_cast<long>(row) * ep.ldadd + col0;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 a4 = reinterpret_cast<const float4*>(ap)[j];
+                v[4 * j] += a4.x; v[4 * j + 1] += a4.y; v[4 * j + 2] += a4.z; v[4 * j + 3] += a4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < ep.n_valid) v[j] += ap[j];
+            }
+          }
+          if (ep.atomic) {
+            float* op = reinterpret_cast<float*>(ep.out) + static_cast<long>(row) * ep.ldo + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < ep.n_valid) atomicAdd(op + j, v[j]);
+          } else if (ep.out_f32) {
+            float* op = reinterpret_cast<float*>(ep.out) + static_cast<long>(row) * ep.ldo + col0;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                reinterpret_cast<float4*>(op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < ep.n_valid) op[j] = v[j];
+            }
+          } else {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(ep.out) + static_cast<long>(row) * ep.ldo + col0;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 q;
+                q.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+                q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                reinterpret_cast<uint4*>(op)[j] = q;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < ep.n_valid) op[j] = __float2bfloat16_rn(v[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int BN, int A_MN, int B_MN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams& ep, int M,
+                       int N, int K, int splits, int max_ctas, cudaStream_t stream) {
+  using S = GemmSmem<BN>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  const int smem_bytes = S::kStages * S::kStageBytes + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    OMLM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured = true;
+  }
+  const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
+  const int work = m_tiles * n_tiles * splits;
+  int grid = num_sms();
+  if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
+  if (work < grid) grid = work;
+  kern<<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmB, ep, M, N, K, splits);
+  OMLM_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace omlm
+
+extern "C" int omlm_gemm_bf16(const void* A, int a_mn_major, long lda, const void* B, int b_mn_major,
+                              long ldb, int M, int N, int K, void* out, int out_f32, long ldo,
+                              const float* addend, long ldadd, float alpha, int splits,
+                              int row_split, int row_valid, int n_valid, int block_n, int max_ctas,
+                              void* stream_) {
+  using namespace omlm;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  OMLM_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem %d x %d x %d", M, N, K);
+  OMLM_CHECK_ARG(block_n == 128 || block_n == 256, "gemm: block_n must be 128 or 256");
+  OMLM_CHECK_ARG(splits >= 1, "gemm: splits must be >= 1");
+  OMLM_CHECK_ARG(splits == 1 || (out_f32 && addend == nullptr), "gemm: split-K needs fp32 atomic output and no addend");
+  if (n_valid <= 0 || n_valid > N) n_valid = N;
+  {  // every split must own at least one k-block (an empty split would publish an unwritten accumulator)
+    const int kb_total = (K + BK - 1) / BK;
+    if (splits > kb_total) splits = kb_total;
+    const int per = (kb_total + splits - 1) / splits;
+    splits = (kb_total + per - 1) / per;
+  }
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (a_mn_major == 0) rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, 64, BM);
+  else                 rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, 64);
+  if (rc) return rc;
+  if (b_mn_major == 0) rc = make_tmap_bf16_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, 64, block_n);
+  else                 rc = make_tmap_bf16_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, 64);
+  if (rc) return rc;
+  EpiParams ep;
+  ep.out = out; ep.addend = addend; ep.ldo = ldo; ep.ldadd = ldadd; ep.alpha = alpha;
+  ep.out_f32 = out_f32; ep.atomic = splits > 1 ? 1 : 0;
+  const long esz = out_f32 ? 4 : 2;
+  ep.vec_ok = ((ldo * esz) % 16 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
+              (addend == nullptr || ((ldadd * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(addend) & 15) == 0));
+  ep.row_split = row_split; ep.row_valid = row_valid; ep.n_valid = n_valid;
+  const int key = (block_n == 256 ? 4 : 0) | (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
+  switch (key) {
+    case 0: return launch_gemm<128, 0, 0>(tmA, tmB, ep, M, N, K, splits, max_ctas, stream);
+    case 1: return launch_gemm<128, 0, 1>(tmA, tmB, ep, M, N, K, splits, max_ctas, stream);
+    case 3: return launch_gemm<128, 1, 1>(tmA, tmB, ep, M, N, K, splits, max_ctas, stream);
+    case 4: return launch_gemm<256, 0, 0>(tmA, tmB, ep, M, N, K, splits, max_ctas, stream);
+    case 5: return launch_gemm<256, 0, 1>(tmA, tmB, ep, M, N, K, splits, max_ctas, stream);
+    case 7: return launch_gemm<256, 1, 1>(tmA, tmB, ep, M, N, K, splits, max_ctas, stream);
+    default:
+      set_last_error("gemm: operand majors (a_mn=%d, b_mn=%d) not instantiated", a_mn_major, b_mn_major);
+      return 1;
+  }
+}

@@ -1,0 +1,81 @@
+"""tcgen05 GEMM (csrc/gemm_tc.cu) vs a plain torch fp32 reference of the same contraction."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12)).item()
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
+@pytest.mark.parametrize("block_n", [128, 256])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (384, 640, 512), (1000, 1032, 520), (128, 128, 64)])
+def test_gemm_majors(a_mn, b_mn, block_n, M, N, K):
+    from open_musiclm_b200 import lib
+    torch.manual_seed(M * 7 + N * 3 + K)
+    dev = "cuda"
+    A = torch.randn(M, K, device=dev).bfloat16()
+    B = torch.randn(N, K, device=dev).bfloat16()
+    ref = A.float() @ B.float().t()
+    a = A.t().contiguous() if a_mn else A
+    b = B.t().contiguous() if b_mn else B
+    for dtype in (torch.bfloat16, torch.float32):
+        out = torch.full((M, N), float("nan"), device=dev, dtype=dtype)
+        lib.gemm(a, b, out, a_mn=a_mn, b_mn=b_mn, block_n=block_n)
+        torch.cuda.synchronize()
+        err = _rel(out, ref)
+        assert err < (6e-3 if dtype == torch.bfloat16 else 1e-5), (a_mn, b_mn, block_n, M, N, K, dtype, err)
+
+
+def test_gemm_residual_and_splitk():
+    from open_musiclm_b200 import lib
+    torch.manual_seed(1)
+    M, N, K = 512, 1024, 2816
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = torch.randn(N, K, device="cuda").bfloat16()
+    X = torch.randn(M, N, device="cuda")
+    ref = X + A.float() @ B.float().t()
+    out = torch.empty_like(X)
+    lib.gemm(A, B, out, addend=X)
+    assert _rel(out, ref) < 1e-5
+    x2 = X.clone()
+    lib.gemm(A, B, x2, addend=x2)  # in place
+    assert _rel(x2, ref) < 1e-5
+    # split-K atomics accumulate on top of existing contents
+    acc = X.clone()
+    lib.gemm(A, B, acc, splits=5)
+    assert _rel(acc, ref) < 1e-5
+    # weight-gradient form: dW[N,K'] = dY[M,N]^T X[M,K'] with both operands MN-major, into a padded layout
+    dY = torch.randn(M, 256, device="cuda").bfloat16()
+    Xa = torch.randn(M, 384, device="cuda").bfloat16()
+    dW = torch.zeros(200, 300, device="cuda")  # canonical (unpadded) gradient: 2 halves of 100 rows, 300 cols
+    lib.gemm(dY, Xa, dW, a_mn=True, b_mn=True, splits=3, row_split=128, row_valid=100, n_valid=300)
+    full = dY.float().t() @ Xa.float()
+    ref_dw = torch.cat([full[0:100, :300], full[128:228, :300]], 0)
+    assert _rel(dW, ref_dw) < 1e-5
+
+
+def test_gemm_large_timing():
+    """Not a benchmark: just makes sure the FFN-up shape of cfg2 runs and is correct on a sample."""
+    from open_musiclm_b200 import lib
+    torch.manual_seed(2)
+    M, N, K = 16384, 5632, 1024
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = torch.randn(N, K, device="cuda").bfloat16()
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    for bn in (128, 256):
+        lib.gemm(A, B, out, block_n=bn)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            lib.gemm(A, B, out, block_n=bn)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        print(f"gemm {M}x{N}x{K} bn={bn}: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.1f} TFLOP/s")
+        idx = torch.randint(0, M, (64,), device="cuda")
+        ref = A[idx].float() @ B.float().t()
+        assert _rel(out[idx], ref) < 6e-3

@@ -197,7 +197,9 @@ def attention(cfg: Cfg, sd, p: str, x, table, key_mask):
     h, dh = cfg.heads, cfg.dim_head
     xn = layer_norm(x, sd[p + "norm.gamma"])                                                    # :250
     q = xn @ sd[p + "to_q.weight"].t()                                                          # :254
-    kv = xn @ sd[p + "to_kv.weight"].t()
+    # NB: kv_input is bound to the PRE-norm x at :228, before `x = self.norm(x)` at :250, so keys and
+    # values are projected from the raw residual stream while queries see the normalised one.
+    kv = x @ sd[p + "to_kv.weight"].t()                                                         # :228, :254
     k, v = kv[..., :dh], kv[..., dh:]
     q = q.view(B, N, h, dh).permute(0, 2, 1, 3)                                                 # :265
     q = q / q.norm(dim=-1, keepdim=True).clamp_min(1e-12) * sd[p + "q_scale"]                   # :269-271, utils.py:68-69
@@ -288,13 +290,15 @@ def forward_logits(cfg: Cfg, sd, ids: Sequence[np.ndarray], key_mask: Optional[n
 
 
 def wrapper_loss(cfg: Cfg, all_logits, labels):
-    """open_musiclm.py:389-410: token-count-weighted CE; the denominator counts ALL sequences."""
+    """open_musiclm.py:389-410: token-count-weighted CE.  num_logits stays 0 for a sequence whose
+    weight is 0 (:395,398-399), so the denominator counts only the weighted sequences."""
     weights = cfg.ce_weights if cfg.ce_weights is not None else [1.0] * len(cfg.seqs)
     total, running = 0, 0.0
     for lg, lb, w in zip(all_logits, labels, weights):
-        n = int(lb.size)
+        n = 0
         loss = 0.0
         if w > 0 and lg is not None:
+            n = int(lb.size)                                                                    # :399
             loss = F.cross_entropy(lg.reshape(-1, lg.shape[-1]), torch.from_numpy(lb).reshape(-1))  # :401
         total += n
         running = running + loss * n * w

@@ -18,6 +18,7 @@ extern "C" {
 #endif
 
 #define OMLM_B200_ABI_VERSION 1
+#define OMLM_MAX_SEQS 4
 
 const char* omlm_last_error(void);
 int omlm_abi_version(void);
@@ -37,6 +38,102 @@ int omlm_gemm_bf16(const void* A, int a_mn_major, long lda, const void* B, int b
                    int M, int N, int K, void* out, int out_f32, long ldo, const float* addend,
                    long ldadd, float alpha, int splits, int row_split, int row_valid, int n_valid,
                    int block_n, int max_ctas, void* stream);
+
+/* ---- integer token path (bit-exact) ------------------------------------------------------------
+ * One pass over the raw ids of all sequences of a TokenConditionedTransformer batch.
+ * Wrapper mode (append_eos=1): eos (= codebook size) appended to every sequence
+ * (open_musiclm.py:346-347, utils.py:112-117); labels = ids incl. eos (:355); drop_last drops the
+ * predicted sequence's last token (:356); mask_cond masks + zeroes conditioning pad/eos ids
+ * (:358-367).  Per position: row of the concatenated embedding table (offset = codebook_size *
+ * (t mod q) added BEFORE the pad test, open_musiclm.py:126-133, utils.py:133-138; -1 = zero row;
+ * start tokens are extra rows) and the key mask (AND mask_in AND forget_keep when given, :373-376).
+ *   ids[s]: int64 [B, len[s]] device pointers (host array of n_seqs pointers)
+ *   ids_out int64 [B, sum n_tok]; src_row int32 [B, N]; key_mask u8 [B, N]; labels int32 [B, sum(len+eos)] or NULL. */
+int omlm_token_plan(int n_seqs, const long long* const* ids, const int* len, const int* codebook,
+                    const int* nq, const int* emb_row_base, const int* start_row, int B,
+                    int append_eos, int drop_last, int mask_cond, int pad_id,
+                    const unsigned char* mask_in, const unsigned char* forget_keep,
+                    long long* ids_out, int* src_row, unsigned char* key_mask, int* labels,
+                    void* stream);
+/* Forgetful causal mask (utils.py:49-56): keep[b,p]=0 for a uniformly random subset of num_drop
+ * positions per row, never position 0.  seed: device pointer; stream_id separates draws. */
+int omlm_forgetful_mask(unsigned char* keep, int B, int N, int num_drop,
+                        const unsigned long long* seed, unsigned long long stream_id, void* stream);
+/* x[m,:] = table[src_row[m],:] (fp32, 128-bit copies); replaces get_embeds + start-token concat
+ * (open_musiclm.py:133-145).  scatter_add is its backward incl. the grad_shrink factor (utils.py:60-61). */
+int omlm_embed_gather(const float* table, const int* src_row, float* x, int M, int D, void* stream);
+int omlm_embed_scatter_add(float* dtable, const int* src_row, const float* dx, int M, int D,
+                           float scale, void* stream);
+
+/* ---- normalisation ------------------------------------------------------------------------------
+ * Bias-less LayerNorm (transformer.py:24-31).  x fp32 [M,D] -> y bf16 [M,D] (row m written to row
+ * dest_row[m] when given, skipped if negative), optional raw bf16 copy of x (keys/values are
+ * projected from the un-normalised stream, transformer.py:228,254), stats[m] = (mean, rstd). */
+int omlm_layernorm_fwd(const float* x, const float* gamma, void* y_bf16, void* xraw_bf16, float* stats,
+                       const int* dest_row, int M, int D, void* stream);
+/* dx = [dres] + [draw] + LN-backward(dy);  dgamma += sum_rows dy * xhat.  dy row for x row m is
+ * src_row[m] when given (-1: no gradient). */
+int omlm_layernorm_bwd(const void* dy_bf16, const float* x, const float* stats, const float* gamma,
+                       const float* dres, const void* draw_bf16, const int* src_row, float* dx,
+                       float* dgamma, int M, int D, void* stream);
+/* l2norm * learned scale on queries / keys (transformer.py:269-271, utils.py:68-69).
+ * q_raw [M, heads*64], kv_raw [M,128] (k | v) -> qn, kvn (k normalised, v copied). */
+int omlm_qk_l2norm_fwd(const void* q_raw, const void* kv_raw, const float* q_scale, const float* k_scale,
+                       void* qn, void* kvn, int M, int heads, void* stream);
+int omlm_qk_l2norm_bwd(const float* dqn, const float* dkvn, const void* q_raw, const void* kv_raw,
+                       const float* q_scale, const float* k_scale, void* dq_raw, void* dkv_raw,
+                       float* dq_scale, float* dk_scale, int M, int heads, void* stream);
+
+/* ---- relative position bias MLP (transformer.py:36-67), fp32 SIMT ------------------------------
+ * C[m,n] (+)= sum_k A[m*sa_m+k*sa_k] B[k*sb_k+n*sb_n] (+bias[n]); act 1 = SiLU (pre-activation to Z). */
+int omlm_sgemm_small(const float* A, long sa_m, long sa_k, const float* B, long sb_k, long sb_n, float* C,
+                     long sc_m, long sc_n, float* Z, const float* bias, int M, int N, int K, int act,
+                     int accumulate, void* stream);
+int omlm_silu_bwd(const float* dA, const float* Z, float* dZ, long n, void* stream);
+int omlm_colsum(const float* X, long s_m, long s_n, float* out, int M, int N, int accumulate, void* stream);
+int omlm_arange_f32(float* out, int n, void* stream);
+
+/* ---- attention (transformer.py:304-331, self-attention, causal, multi-query) -------------------
+ * qn [B,N,heads*64] bf16, kvn [B,N,128] bf16, table fp32 [heads, table_ld] (bias for i-j >= 0),
+ * key_mask u8 [B,N] or NULL -> out bf16 [B,N,heads*64], lse2 fp32 [B,N*heads] (log2 domain). */
+int omlm_attn_fwd(const void* qn, const void* kvn, const float* table, int table_ld,
+                  const unsigned char* key_mask, void* out, float* lse2, int B, int N, int heads,
+                  float scale, void* stream);
+/* Accumulates (+=) into dqn fp32 [B,N,heads*64], dkvn fp32 [B,N,128], dtable fp32 [heads,table_ld]. */
+int omlm_attn_bwd(const void* qn, const void* kvn, const void* d_o, const void* o, const float* lse2,
+                  const float* table, int table_ld, const unsigned char* key_mask, float* dsum_scratch,
+                  float* dqn, float* dkvn, float* dtable, int B, int N, int heads, float scale,
+                  void* stream);
+
+/* ---- ConvFeedForward middle (transformer.py:122-150): conv k=3 -> GEGLU -> LN(F) -> dropout ----
+ * u bf16 [B*N, 2Fp] (value half | gate half), conv_w fp32 [2Fp,3], gamma fp32 [Fp] (packed/padded)
+ * -> hn bf16 [B*N, Fp], stats fp32 [B*N, 2]. */
+int omlm_ffn_mid_fwd(const void* u, const float* conv_w, const float* gamma, void* hn, float* stats, int B,
+                     int N, int F, int Fp, float drop_p, const unsigned long long* seed, int layer,
+                     void* stream);
+/* dhn -> du bf16 [B*N, 2Fp]; dgamma [Fp] += ; dconv_w [2Fp,3] += ; dy_scratch bf16 [B*N, 2Fp]. */
+int omlm_ffn_mid_bwd(const void* dhn, const void* u, const float* stats, const float* conv_w, const float* gamma,
+                     void* dy_scratch, void* du, float* dgamma, float* dconv_w, int B, int N, int F, int Fp,
+                     float drop_p, const unsigned long long* seed, int layer, void* stream);
+
+/* ---- cross entropy (open_musiclm.py:401) --------------------------------------------------------
+ * loss_acc[0] += sum of row losses, loss_acc[1] += rows counted; dlogits bf16 [rows, ldd] =
+ * (softmax - onehot) * grad_scale, zero in columns [C, Cp). */
+int omlm_cross_entropy(const float* logits, long ld, const int* labels, int label_stride, int rows,
+                       int C, int ignore_index, float grad_scale, void* dlogits_bf16, long ldd,
+                       int Cp, float* loss_acc, void* stream);
+
+/* ---- optimiser (trainer.py:443-449, optimizer.py:3-34) ------------------------------------------
+ * hyper (device, 9 floats): lr, beta1, beta2, eps, wd, 1-beta1^t, 1-beta2^t, max_grad_norm, grad prescale.
+ * The arena is ordered [weight-decayed params | others]; n_decay = size of the first part. */
+int omlm_grad_sumsq(const float* g, long n, float prescale, double* acc, void* stream);
+int omlm_adamw_step(float* p, const float* g, float* m, float* v, long n, long n_decay, const float* hyper,
+                    const double* sumsq, void* stream);
+/* canonical fp32 -> padded compute layout (bf16 or fp32) and gradient unpacking (+=). */
+int omlm_pack(const float* src, long src_ld, int rows_valid, int cols_valid, void* dst, int dst_f32, long dst_ld,
+              int rows_p, int cols_p, int split_dst, int split_src, void* stream);
+int omlm_unpack_add(const float* packed, long p_ld, int rows_p, int cols_p, float* dst, long dst_ld, int rows_valid,
+                    int cols_valid, int split_dst, int split_src, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,387 @@
+// Bias-less LayerNorm (forward / backward) and the cosine-attention l2norm * scale (forward / backward).
+// HBM-bound kernels: one warp per row, 128-bit vectorised accesses, row cached in registers.
+//
+// Replaces  LayerNorm.forward        open_musiclm/transformer.py:24-31  (F.layer_norm, eps 1e-5, beta == 0)
+//           l2norm + q/k scale        open_musiclm/transformer.py:269-271, utils.py:68-69
+#include "common.cuh"
+#include "../../include/omlm_b200.h"
+
+namespace omlm {
+
+constexpr int kNormThreads = 256;  // 8 rows per block
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm forward: y = (x - mean) * rstd * gamma  -> bf16;  optional raw bf16 copy of x;
+// stats[m] = (mean, rstd).  NCHUNK * 128 >= D.
+template <int NCHUNK>
+__global__ void __launch_bounds__(kNormThreads)
+layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                     __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ xraw,
+                     float2* __restrict__ stats, const int* __restrict__ dest_row, int M, int D) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (kNormThreads / 32) + warp;
+  if (row >= M) return;
+  const float* xr = x + static_cast<long long>(row) * D;
+  float4 v[NCHUNK];
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) {
+    const int col = (c * 32 + lane) * 4;
+    v[c] = (col < D) ? *reinterpret_cast<const float4*>(xr + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+    sum += v[c].x + v[c].y + v[c].z + v[c].w;
+  }
+  const float mean = warp_sum(sum) / D;
+  float sq = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) {
+    const int col = (c * 32 + lane) * 4;
+    if (col < D) {
+      const float a = v[c].x - mean, b = v[c].y - mean, cc = v[c].z - mean, d = v[c].w - mean;
+      sq += a * a + b * b + cc * cc + d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / D + 1e-5f);
+  if (lane == 0 && stats != nullptr) stats[row] = make_float2(mean, rstd);
+  long long orow = row;
+  if (dest_row != nullptr) orow = dest_row[row];
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) {
+    const int col = (c * 32 + lane) * 4;
+    if (col < D) {
+      if (orow >= 0) {
+        const float4 g = *reinterpret_cast<const float4*>(gamma + col);
+        uint2 o;
+        o.x = pack_bf16x2((v[c].x - mean) * rstd * g.x, (v[c].y - mean) * rstd * g.y);
+        o.y = pack_bf16x2((v[c].z - mean) * rstd * g.z, (v[c].w - mean) * rstd * g.w);
+        *reinterpret_cast<uint2*>(y + orow * D + col) = o;
+      }
+      if (xraw != nullptr) {
+        uint2 o;
+        o.x = pack_bf16x2(v[c].x, v[c].y);
+        o.y = pack_bf16x2(v[c].z, v[c].w);
+        *reinterpret_cast<uint2*>(xraw + static_cast<long long>(row) * D + col) = o;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward.  dx = [dres] + [draw] + rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat))
+// dgamma[col] += sum_rows dy * xhat  (fp32 atomics, one per column per block).
+// dy rows may be permuted (src_row: row of dy for this x row, -1 = no gradient).
+template <int NCHUNK>
+__global__ void __launch_bounds__(kNormThreads)
+layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
+                     const float2* __restrict__ stats, const float* __restrict__ gamma,
+                     const float* __restrict__ dres, const __nv_bfloat16* __restrict__ draw,
+                     const int* __restrict__ src_row, float* __restrict__ dx,
+                     float* __restrict__ dgamma, int M, int D, int rows_per_block) {
+  __shared__ float sdg[NCHUNK * 128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < NCHUNK * 128; i += kNormThreads) sdg[i] = 0.f;
+  __syncthreads();
+  float4 dg[NCHUNK];
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) dg[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int row0 = blockIdx.x * rows_per_block;
+  const int row1 = min(M, row0 + rows_per_block);
+  for (int row = row0 + warp; row < row1; row += kNormThreads / 32) {
+    const float2 st = stats[row];
+    const float* xr = x + static_cast<long long>(row) * D;
+    long long drow = row;
+    if (src_row != nullptr) drow = src_row[row];
+    float4 gd[NCHUNK], xh[NCHUNK];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) {
+      const int col = (c * 32 + lane) * 4;
+      gd[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      xh[c] = gd[c];
+      if (col < D && drow >= 0) {
+        const float4 xv = *reinterpret_cast<const float4*>(xr + col);
+        const uint2 dv = *reinterpret_cast<const uint2*>(dy + drow * D + col);
+        const float4 g = *reinterpret_cast<const float4*>(gamma + col);
+        const float2 d01 = unpack_bf16x2(dv.x), d23 = unpack_bf16x2(dv.y);
+        xh[c] = make_float4((xv.x - st.x) * st.y, (xv.y - st.x) * st.y, (xv.z - st.x) * st.y, (xv.w - st.x) * st.y);
+        dg[c].x += d01.x * xh[c].x; dg[c].y += d01.y * xh[c].y; dg[c].z += d23.x * xh[c].z; dg[c].w += d23.y * xh[c].w;
+        gd[c] = make_float4(d01.x * g.x, d01.y * g.y, d23.x * g.z, d23.y * g.w);
+        s1 += gd[c].x + gd[c].y + gd[c].z + gd[c].w;
+        s2 += gd[c].x * xh[c].x + gd[c].y * xh[c].y + gd[c].z * xh[c].z + gd[c].w * xh[c].w;
+      }
+    }
+    s1 = warp_sum(s1) / D;
+    s2 = warp_sum(s2) / D;
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) {
+      const int col = (c * 32 + lane) * 4;
+      if (col < D) {
+        float4 o;
+        o.x = st.y * (gd[c].x - s1 - xh[c].x * s2);
+        o.y = st.y * (gd[c].y - s1 - xh[c].y * s2);
+        o.z = st.y * (gd[c].z - s1 - xh[c].z * s2);
+        o.w = st.y * (gd[c].w - s1 - xh[c].w * s2);
+        if (dres != nullptr) {
+          const float4 r = *reinterpret_cast<const float4*>(dres + static_cast<long long>(row) * D + col);
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        if (draw != nullptr) {
+          const uint2 rv = *reinterpret_cast<const uint2*>(draw + static_cast<long long>(row) * D + col);
+          const float2 r01 = unpack_bf16x2(rv.x), r23 = unpack_bf16x2(rv.y);
+          o.x += r01.x; o.y += r01.y; o.z += r23.x; o.w += r23.y;
+        }
+        *reinterpret_cast<float4*>(dx + static_cast<long long>(row) * D + col) = o;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) {
+    const int col = (c * 32 + lane) * 4;
+    atomicAdd(&sdg[col + 0], dg[c].x);
+    atomicAdd(&sdg[col + 1], dg[c].y);
+    atomicAdd(&sdg[col + 2], dg[c].z);
+    atomicAdd(&sdg[col + 3], dg[c].w);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += kNormThreads) atomicAdd(&dgamma[i], sdg[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// l2norm * scale forward.  Vectors of 64 bf16; 8 lanes per vector (16 bytes each).
+// per row: h query heads (from q_raw), 1 key (kv_raw[:, :64]) normalised; value (kv_raw[:, 64:]) copied.
+__global__ void __launch_bounds__(256)
+qk_l2norm_fwd_kernel(const __nv_bfloat16* __restrict__ q_raw, const __nv_bfloat16* __restrict__ kv_raw,
+                     const float* __restrict__ q_scale, const float* __restrict__ k_scale,
+                     __nv_bfloat16* __restrict__ qn, __nv_bfloat16* __restrict__ kvn, int M, int h) {
+  const long long gvec = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
+  const int sub = threadIdx.x & 7;
+  const int per_row = h + 2;
+  const long long total = static_cast<long long>(M) * per_row;
+  const bool active = gvec < total;
+  const long long row = active ? gvec / per_row : 0;
+  const int j = active ? static_cast<int>(gvec - row * per_row) : 0;
+  const __nv_bfloat16* src;
+  __nv_bfloat16* dst;
+  const float* sc = nullptr;
+  if (j < h) { src = q_raw + row * (h * 64) + j * 64; dst = qn + row * (h * 64) + j * 64; sc = q_scale; }
+  else if (j == h) { src = kv_raw + row * 128; dst = kvn + row * 128; sc = k_scale; }
+  else { src = kv_raw + row * 128 + 64; dst = kvn + row * 128 + 64; }
+  uint4 raw = make_uint4(0, 0, 0, 0);
+  if (active) raw = *reinterpret_cast<const uint4*>(src + sub * 8);
+  float f[8];
+  { float2 t;
+    t = unpack_bf16x2(raw.x); f[0] = t.x; f[1] = t.y;
+    t = unpack_bf16x2(raw.y); f[2] = t.x; f[3] = t.y;
+    t = unpack_bf16x2(raw.z); f[4] = t.x; f[5] = t.y;
+    t = unpack_bf16x2(raw.w); f[6] = t.x; f[7] = t.y; }
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
+  ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+  ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+  ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+  if (!active) return;
+  if (sc != nullptr) {
+    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps
+    const float4 s0 = *reinterpret_cast<const float4*>(sc + sub * 8);
+    const float4 s1 = *reinterpret_cast<const float4*>(sc + sub * 8 + 4);
+    uint4 o;
+    o.x = pack_bf16x2(f[0] * inv * s0.x, f[1] * inv * s0.y);
+    o.y = pack_bf16x2(f[2] * inv * s0.z, f[3] * inv * s0.w);
+    o.z = pack_bf16x2(f[4] * inv * s1.x, f[5] * inv * s1.y);
+    o.w = pack_bf16x2(f[6] * inv * s1.z, f[7] * inv * s1.w);
+    *reinterpret_cast<uint4*>(dst + sub * 8) = o;
+  } else {
+    *reinterpret_cast<uint4*>(dst + sub * 8) = raw;
+  }
+}
+
+// l2norm * scale backward.  y = s * x/|x|.  dx = (s*dy - xh * (xh . s*dy)) / |x| ;  ds += dy * xh.
+// dqn: fp32 [M, h*64] (atomically accumulated by the attention backward); dkvn: fp32 [M, 128].
+// Outputs bf16 dq_raw [M, h*64], dkv_raw [M, 128] (value gradient passes through).
+__global__ void __launch_bounds__(256)
+qk_l2norm_bwd_kernel(const float* __restrict__ dqn, const float* __restrict__ dkvn,
+                     const __nv_bfloat16* __restrict__ q_raw, const __nv_bfloat16* __restrict__ kv_raw,
+                     const float* __restrict__ q_scale, const float* __restrict__ k_scale,
+                     __nv_bfloat16* __restrict__ dq_raw, __nv_bfloat16* __restrict__ dkv_raw,
+                     float* __restrict__ dq_scale, float* __restrict__ dk_scale, int M, int h) {
+  __shared__ float sds[2][64];
+  if (threadIdx.x < 128) sds[threadIdx.x >> 6][threadIdx.x & 63] = 0.f;
+  __syncthreads();
+  const int sub = threadIdx.x & 7;
+  const int per_row = h + 2;
+  const long long total = static_cast<long long>(M) * per_row;
+  float dsq[8], dsk[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { dsq[i] = 0.f; dsk[i] = 0.f; }
+  for (long long base = static_cast<long long>(blockIdx.x) * (blockDim.x >> 3); base < total;
+       base += static_cast<long long>(gridDim.x) * (blockDim.x >> 3)) {
+    const long long gvec = base + (threadIdx.x >> 3);
+    const bool active = gvec < total;
+    const long long row = active ? gvec / per_row : 0;
+    const int j = active ? static_cast<int>(gvec - row * per_row) : 0;
+    const __nv_bfloat16* src;
+    const float* dsrc;
+    __nv_bfloat16* dst;
+    const float* sc = nullptr;
+    if (j < h) { src = q_raw + row * (h * 64) + j * 64; dsrc = dqn + row * (h * 64) + j * 64; dst = dq_raw + row * (h * 64) + j * 64; sc = q_scale; }
+    else if (j == h) { src = kv_raw + row * 128; dsrc = dkvn + row * 128; dst = dkv_raw + row * 128; sc = k_scale; }
+    else { src = kv_raw + row * 128 + 64; dsrc = dkvn + row * 128 + 64; dst = dkv_raw + row * 128 + 64; }
+    float f[8], g[8];
+    if (active) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(src + sub * 8);
+      float2 t;
+      t = unpack_bf16x2(raw.x); f[0] = t.x; f[1] = t.y;
+      t = unpack_bf16x2(raw.y); f[2] = t.x; f[3] = t.y;
+      t = unpack_bf16x2(raw.z); f[4] = t.x; f[5] = t.y;
+      t = unpack_bf16x2(raw.w); f[6] = t.x; f[7] = t.y;
+      const float4 g0 = *reinterpret_cast<const float4*>(dsrc + sub * 8);
+      const float4 g1 = *reinterpret_cast<const float4*>(dsrc + sub * 8 + 4);
+      g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { f[i] = 0.f; g[i] = 0.f; }
+    }
+    float o[8];
+    {
+      // all 32 lanes run the same shuffles; the value vectors (sc == nullptr) just discard the result
+      const bool norm = (sc != nullptr);
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
+      ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+      const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+      float s[8];
+      if (norm) {
+        const float4 s0 = *reinterpret_cast<const float4*>(sc + sub * 8);
+        const float4 s1 = *reinterpret_cast<const float4*>(sc + sub * 8 + 4);
+        s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w; s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] = 1.f;
+      }
+      float dot = 0.f, xh[8], sg[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        xh[i] = f[i] * inv;
+        if (norm) { if (j < h) dsq[i] += g[i] * xh[i]; else dsk[i] += g[i] * xh[i]; }
+        sg[i] = g[i] * s[i];
+        dot += xh[i] * sg[i];
+      }
+      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = norm ? (sg[i] - xh[i] * dot) * inv : g[i];
+    }
+    if (active) {
+      uint4 ov;
+      ov.x = pack_bf16x2(o[0], o[1]); ov.y = pack_bf16x2(o[2], o[3]);
+      ov.z = pack_bf16x2(o[4], o[5]); ov.w = pack_bf16x2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(dst + sub * 8) = ov;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    atomicAdd(&sds[0][sub * 8 + i], dsq[i]);
+    atomicAdd(&sds[1][sub * 8 + i], dsk[i]);
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) atomicAdd(&dq_scale[threadIdx.x], sds[0][threadIdx.x]);
+  else if (threadIdx.x < 128) atomicAdd(&dk_scale[threadIdx.x - 64], sds[1][threadIdx.x - 64]);
+}
+
+template <int NCHUNK>
+static int launch_ln_fwd(const float* x, const float* gamma, __nv_bfloat16* y, __nv_bfloat16* xraw,
+                         float2* stats, const int* dest_row, int M, int D, cudaStream_t st) {
+  const int rows_per_block = kNormThreads / 32;
+  layernorm_fwd_kernel<NCHUNK><<<(M + rows_per_block - 1) / rows_per_block, kNormThreads, 0, st>>>(
+      x, gamma, y, xraw, stats, dest_row, M, D);
+  OMLM_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int NCHUNK>
+static int launch_ln_bwd(const __nv_bfloat16* dy, const float* x, const float2* stats, const float* gamma,
+                         const float* dres, const __nv_bfloat16* draw, const int* src_row, float* dx,
+                         float* dgamma, int M, int D, cudaStream_t st) {
+  // ~4 blocks per SM; each block walks a contiguous slab of rows and flushes dgamma once.
+  int blocks = num_sms() * 4;
+  int rows_per_block = (M + blocks - 1) / blocks;
+  if (rows_per_block < 8) rows_per_block = 8;
+  blocks = (M + rows_per_block - 1) / rows_per_block;
+  layernorm_bwd_kernel<NCHUNK><<<blocks, kNormThreads, 0, st>>>(dy, x, stats, gamma, dres, draw, src_row, dx,
+                                                               dgamma, M, D, rows_per_block);
+  OMLM_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace omlm
+
+extern "C" {
+
+int omlm_layernorm_fwd(const float* x, const float* gamma, void* y_bf16, void* xraw_bf16, float* stats,
+                       const int* dest_row, int M, int D, void* stream) {
+  using namespace omlm;
+  OMLM_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0 && D <= 2048, "layernorm_fwd: unsupported shape %d x %d", M, D);
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  auto y = reinterpret_cast<__nv_bfloat16*>(y_bf16);
+  auto xr = reinterpret_cast<__nv_bfloat16*>(xraw_bf16);
+  auto s2 = reinterpret_cast<float2*>(stats);
+  const int nchunk = (D + 127) / 128;
+  if (nchunk <= 1) return launch_ln_fwd<1>(x, gamma, y, xr, s2, dest_row, M, D, st);
+  if (nchunk <= 2) return launch_ln_fwd<2>(x, gamma, y, xr, s2, dest_row, M, D, st);
+  if (nchunk <= 4) return launch_ln_fwd<4>(x, gamma, y, xr, s2, dest_row, M, D, st);
+  if (nchunk <= 8) return launch_ln_fwd<8>(x, gamma, y, xr, s2, dest_row, M, D, st);
+  return launch_ln_fwd<16>(x, gamma, y, xr, s2, dest_row, M, D, st);
+}
+
+int omlm_layernorm_bwd(const void* dy_bf16, const float* x, const float* stats, const float* gamma,
+                       const float* dres, const void* draw_bf16, const int* src_row, float* dx,
+                       float* dgamma, int M, int D, void* stream) {
+  using namespace omlm;
+  OMLM_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0 && D <= 2048, "layernorm_bwd: unsupported shape %d x %d", M, D);
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  auto dy = reinterpret_cast<const __nv_bfloat16*>(dy_bf16);
+  auto dr = reinterpret_cast<const __nv_bfloat16*>(draw_bf16);
+  auto s2 = reinterpret_cast<const float2*>(stats);
+  const int nchunk = (D + 127) / 128;
+  if (nchunk <= 1) return launch_ln_bwd<1>(dy, x, s2, gamma, dres, dr, src_row, dx, dgamma, M, D, st);
+  if (nchunk <= 2) return launch_ln_bwd<2>(dy, x, s2, gamma, dres, dr, src_row, dx, dgamma, M, D, st);
+  if (nchunk <= 4) return launch_ln_bwd<4>(dy, x, s2, gamma, dres, dr, src_row, dx, dgamma, M, D, st);
+  if (nchunk <= 8) return launch_ln_bwd<8>(dy, x, s2, gamma, dres, dr, src_row, dx, dgamma, M, D, st);
+  return launch_ln_bwd<16>(dy, x, s2, gamma, dres, dr, src_row, dx, dgamma, M, D, st);
+}
+
+int omlm_qk_l2norm_fwd(const void* q_raw, const void* kv_raw, const float* q_scale, const float* k_scale,
+                       void* qn, void* kvn, int M, int heads, void* stream) {
+  using namespace omlm;
+  OMLM_CHECK_ARG(M > 0 && heads > 0, "qk_l2norm_fwd: bad shape");
+  const long long total = static_cast<long long>(M) * (heads + 2);
+  const int blocks = static_cast<int>((total * 8 + 255) / 256);
+  qk_l2norm_fwd_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(q_raw), reinterpret_cast<const __nv_bfloat16*>(kv_raw), q_scale,
+      k_scale, reinterpret_cast<__nv_bfloat16*>(qn), reinterpret_cast<__nv_bfloat16*>(kvn), M, heads);
+  OMLM_LAUNCH_CHECK();
+  return 0;
+}
+
+int omlm_qk_l2norm_bwd(const float* dqn, const float* dkvn, const void* q_raw, const void* kv_raw,
+                       const float* q_scale, const float* k_scale, void* dq_raw, void* dkv_raw,
+                       float* dq_scale, float* dk_scale, int M, int heads, void* stream) {
+  using namespace omlm;
+  OMLM_CHECK_ARG(M > 0 && heads > 0, "qk_l2norm_bwd: bad shape");
+  const long long total = static_cast<long long>(M) * (heads + 2);
+  long long blocks = (total + 31) / 32;
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  qk_l2norm_bwd_kernel<<<static_cast<int>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      dqn, dkvn, reinterpret_cast<const __nv_bfloat16*>(q_raw), reinterpret_cast<const __nv_bfloat16*>(kv_raw),
+      q_scale, k_scale, reinterpret_cast<__nv_bfloat16*>(dq_raw), reinterpret_cast<__nv_bfloat16*>(dkv_raw),
+      dq_scale, dk_scale, M, heads);
+  OMLM_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,143 @@
+// Optimiser step on the flat fp32 parameter/gradient arena + (un)packing between the canonical
+// (state_dict) parameter layout and the padded bf16 compute layout.
+//
+// Replaces  clip_grad_norm_(0.5) + AdamW.step (trainer.py:443-449, optimizer.py:3-34: weight decay only
+// on ndim >= 2 parameters, betas (0.9, 0.99), eps 1e-8).  The arena is ordered [decayed | non-decayed],
+// so the decay rule is a single index compare.  Clip coefficient and hyper-parameters are read from
+// device memory: the step never synchronises with the host.
+#include "common.cuh"
+#include "../../include/omlm_b200.h"
+
+namespace omlm {
+
+// acc[0] (double) += sum (g * prescale)^2
+__global__ void __launch_bounds__(512)
+sumsq_kernel(const float* __restrict__ g, long n, float prescale, double* __restrict__ acc) {
+  float s = 0.f;
+  const long n4 = n >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float4 v = g4[i];
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { const float v = g[(n4 << 2) + threadIdx.x]; s += v * v; }
+  __shared__ float red[16];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < 16 ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(acc, static_cast<double>(v) * prescale * prescale);
+  }
+}
+
+// hyper: [0] lr  [1] beta1  [2] beta2  [3] eps  [4] weight_decay  [5] 1-beta1^t  [6] 1-beta2^t
+//        [7] max_grad_norm (<=0: no clipping)  [8] grad prescale (1/world for DDP-mean)
+__global__ void __launch_bounds__(512)
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+             long n, long n_decay, const float* __restrict__ hyper, const double* __restrict__ sumsq) {
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
+  const float bc1 = hyper[5], bc2 = hyper[6], max_norm = hyper[7], prescale = hyper[8];
+  float coef = prescale;
+  if (max_norm > 0.f) {
+    const float norm = static_cast<float>(sqrt(*sumsq));
+    coef *= fminf(1.f, max_norm / (norm + 1e-6f));  // torch.nn.utils.clip_grad_norm_
+  }
+  const float step_size = lr / bc1;
+  const float inv_sqrt_bc2 = rsqrtf(bc2);
+  const float decay = 1.f - lr * wd;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * coef;
+    float pi = p[i];
+    if (i < n_decay) pi *= decay;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    p[i] = pi - step_size * (mi / denom);
+  }
+}
+
+// dst[r, c] = src[map(r), c] for c < cols_valid and live r, else 0.
+// map: if split_dst > 0: half = r / split_dst, rr = r % split_dst, live iff rr < split_src, src row = half*split_src + rr
+//      else live iff r < rows_valid.
+template <typename OutT>
+__global__ void pack_kernel(const float* __restrict__ src, long src_ld, int rows_valid, int cols_valid,
+                            OutT* __restrict__ dst, long dst_ld, int rows_p, int cols_p, int split_dst, int split_src) {
+  const long total = static_cast<long>(rows_p) * cols_p;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / cols_p), c = static_cast<int>(i - static_cast<long>(r) * cols_p);
+    int sr = r; bool live = r < rows_valid;
+    if (split_dst > 0) { const int half = r / split_dst, rr = r - half * split_dst; live = rr < split_src; sr = half * split_src + rr; live = live && sr < rows_valid; }
+    float val = 0.f;
+    if (live && c < cols_valid) val = src[sr * src_ld + c];
+    if constexpr (sizeof(OutT) == 2) dst[r * dst_ld + c] = __float2bfloat16_rn(val);
+    else dst[r * dst_ld + c] = val;
+  }
+}
+
+// canonical[map(r), c] += packed[r, c]  (inverse of pack for fp32 gradients)
+__global__ void unpack_add_kernel(const float* __restrict__ packed, long p_ld, int rows_p, int cols_p,
+                                  float* __restrict__ dst, long dst_ld, int rows_valid, int cols_valid,
+                                  int split_dst, int split_src) {
+  const long total = static_cast<long>(rows_p) * cols_p;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / cols_p), c = static_cast<int>(i - static_cast<long>(r) * cols_p);
+    int sr = r; bool live = r < rows_valid;
+    if (split_dst > 0) { const int half = r / split_dst, rr = r - half * split_dst; live = rr < split_src; sr = half * split_src + rr; live = live && sr < rows_valid; }
+    if (live && c < cols_valid) dst[sr * dst_ld + c] += packed[r * p_ld + c];
+  }
+}
+
+}  // namespace omlm
+
+extern "C" {
+
+int omlm_grad_sumsq(const float* g, long n, float prescale, double* acc, void* stream) {
+  using namespace omlm;
+  OMLM_CHECK_ARG(n > 0, "grad_sumsq: empty");
+  OMLM_CHECK_ARG((reinterpret_cast<uintptr_t>(g) & 15) == 0, "grad_sumsq: arena must be 16B aligned");
+  const int blocks = static_cast<int>(std::min<long>((n / 4 + 511) / 512 + 1, static_cast<long>(num_sms()) * 4));
+  sumsq_kernel<<<blocks, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(g, n, prescale, acc);
+  OMLM_LAUNCH_CHECK();
+  return 0;
+}
+
+int omlm_adamw_step(float* p, const float* g, float* m, float* v, long n, long n_decay, const float* hyper,
+                    const double* sumsq, void* stream) {
+  using namespace omlm;
+  OMLM_CHECK_ARG(n > 0 && n_decay >= 0 && n_decay <= n, "adamw_step: bad sizes");
+  const int blocks = static_cast<int>(std::min<long>((n + 511) / 512, static_cast<long>(num_sms()) * 8));
+  adamw_kernel<<<blocks, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, n_decay, hyper, sumsq);
+  OMLM_LAUNCH_CHECK();
+  return 0;
+}
+
+int omlm_pack(const float* src, long src_ld, int rows_valid, int cols_valid, void* dst, int dst_f32, long dst_ld,
+              int rows_p, int cols_p, int split_dst, int split_src, void* stream) {
+  using namespace omlm;
+  OMLM_CHECK_ARG(rows_p > 0 && cols_p > 0, "pack: empty");
+  const long total = static_cast<long>(rows_p) * cols_p;
+  const int blocks = static_cast<int>(std::min<long>((total + 255) / 256, static_cast<long>(num_sms()) * 8));
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  if (dst_f32)
+    pack_kernel<float><<<blocks, 256, 0, st>>>(src, src_ld, rows_valid, cols_valid, reinterpret_cast<float*>(dst), dst_ld, rows_p, cols_p, split_dst, split_src);
+  else
+    pack_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(src, src_ld, rows_valid, cols_valid, reinterpret_cast<__nv_bfloat16*>(dst), dst_ld, rows_p, cols_p, split_dst, split_src);
+  OMLM_LAUNCH_CHECK();
+  return 0;
+}
+
+int omlm_unpack_add(const float* packed, long p_ld, int rows_p, int cols_p, float* dst, long dst_ld, int rows_valid,
+                    int cols_valid, int split_dst, int split_src, void* stream) {
+  using namespace omlm;
+  OMLM_CHECK_ARG(rows_p > 0 && cols_p > 0, "unpack_add: empty");
+  const long total = static_cast<long>(rows_p) * cols_p;
+  const int blocks = static_cast<int>(std::min<long>((total + 255) / 256, static_cast<long>(num_sms()) * 8));
+  unpack_add_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(packed, p_ld, rows_p, cols_p, dst, dst_ld, rows_valid, cols_valid, split_dst, split_src);
+  OMLM_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -90,3 +90,132 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, M=None, N=None, K=None, addend=No
          _p(addend), _L(addend.stride(0) if addend is not None else 0), _F(alpha), _I(splits),
          _I(row_split), _I(row_valid), _I(n_valid), _I(block_n), _I(max_ctas), _stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# thin tensor-level wrappers (tensors in, raw pointers out); shapes are validated on the C side
+# ------------------------------------------------------------------------------------------------
+_ULL = ctypes.c_ulonglong
+
+
+def token_plan(ids_list, codebooks, nqs, emb_row_base, start_row, *, append_eos, drop_last, mask_cond,
+               pad_id=-1, mask_in=None, forget_keep=None, want_labels=True):
+    """Returns ids_out [B, sum n_tok] int64, src_row [B,N] int32, key_mask [B,N] uint8, labels [B, sum(len+eos)] int32."""
+    S = len(ids_list)
+    B = ids_list[0].shape[0]
+    dev = ids_list[0].device
+    flat = [t.reshape(B, -1).contiguous() for t in ids_list]
+    assert all(t.dtype == torch.int64 for t in flat)
+    lens = [t.shape[1] for t in flat]
+    n_tok = [l + (1 if append_eos else 0) - (1 if (drop_last and s == S - 1) else 0) for s, l in enumerate(lens)]
+    N = sum(n + 1 for n in n_tok)
+    ids_out = torch.empty(B, sum(n_tok), dtype=torch.int64, device=dev)
+    src_row = torch.empty(B, N, dtype=torch.int32, device=dev)
+    key_mask = torch.empty(B, N, dtype=torch.uint8, device=dev)
+    n_lab = sum(l + (1 if append_eos else 0) for l in lens)
+    labels = torch.empty(B, n_lab, dtype=torch.int32, device=dev) if want_labels else None
+    ptrs = (ctypes.c_void_p * S)(*[t.data_ptr() for t in flat])
+    arr = lambda v: (ctypes.c_int * S)(*[int(x) for x in v])
+    call("omlm_token_plan", _I(S), ptrs, arr(lens), arr(codebooks), arr(nqs), arr(emb_row_base), arr(start_row),
+         _I(B), _I(int(append_eos)), _I(int(drop_last)), _I(int(mask_cond)), _I(pad_id), _p(mask_in), _p(forget_keep),
+         _p(ids_out), _p(src_row), _p(key_mask), _p(labels), _stream())
+    return ids_out, src_row, key_mask, labels, n_tok
+
+
+def forgetful_mask(B, N, num_drop, seed_tensor, stream_id, device):
+    keep = torch.empty(B, N, dtype=torch.uint8, device=device)
+    call("omlm_forgetful_mask", _p(keep), _I(B), _I(N), _I(num_drop), _p(seed_tensor), _ULL(stream_id), _stream())
+    return keep
+
+
+def embed_gather(table, src_row, x):
+    M, D = x.shape
+    call("omlm_embed_gather", _p(table), _p(src_row), _p(x), _I(M), _I(D), _stream())
+
+
+def embed_scatter_add(dtable, src_row, dx, scale):
+    M, D = dx.shape
+    call("omlm_embed_scatter_add", _p(dtable), _p(src_row), _p(dx), _I(M), _I(D), _F(scale), _stream())
+
+
+def layernorm_fwd(x, gamma, y, xraw=None, stats=None, dest_row=None):
+    M, D = x.shape
+    call("omlm_layernorm_fwd", _p(x), _p(gamma), _p(y), _p(xraw), _p(stats), _p(dest_row), _I(M), _I(D), _stream())
+
+
+def layernorm_bwd(dy, x, stats, gamma, dx, dgamma, dres=None, draw=None, src_row=None):
+    M, D = x.shape
+    call("omlm_layernorm_bwd", _p(dy), _p(x), _p(stats), _p(gamma), _p(dres), _p(draw), _p(src_row), _p(dx),
+         _p(dgamma), _I(M), _I(D), _stream())
+
+
+def qk_l2norm_fwd(q_raw, kv_raw, q_scale, k_scale, qn, kvn, heads):
+    call("omlm_qk_l2norm_fwd", _p(q_raw), _p(kv_raw), _p(q_scale), _p(k_scale), _p(qn), _p(kvn),
+         _I(q_raw.shape[0]), _I(heads), _stream())
+
+
+def qk_l2norm_bwd(dqn, dkvn, q_raw, kv_raw, q_scale, k_scale, dq_raw, dkv_raw, dq_scale, dk_scale, heads):
+    call("omlm_qk_l2norm_bwd", _p(dqn), _p(dkvn), _p(q_raw), _p(kv_raw), _p(q_scale), _p(k_scale), _p(dq_raw),
+         _p(dkv_raw), _p(dq_scale), _p(dk_scale), _I(q_raw.shape[0]), _I(heads), _stream())
+
+
+def sgemm_small(A, sa, B, sb, C, sc, M, N, K, *, Z=None, bias=None, act=0, accumulate=False):
+    call("omlm_sgemm_small", _p(A), _L(sa[0]), _L(sa[1]), _p(B), _L(sb[0]), _L(sb[1]), _p(C), _L(sc[0]), _L(sc[1]),
+         _p(Z), _p(bias), _I(M), _I(N), _I(K), _I(act), _I(int(accumulate)), _stream())
+
+
+def silu_bwd(dA, Z, dZ):
+    call("omlm_silu_bwd", _p(dA), _p(Z), _p(dZ), _L(dA.numel()), _stream())
+
+
+def colsum(X, s_m, s_n, out, M, N, accumulate=False):
+    call("omlm_colsum", _p(X), _L(s_m), _L(s_n), _p(out), _I(M), _I(N), _I(int(accumulate)), _stream())
+
+
+def arange_f32(out):
+    call("omlm_arange_f32", _p(out), _I(out.numel()), _stream())
+
+
+def attn_fwd(qn, kvn, table, key_mask, out, lse2, B, N, heads, scale=8.0):
+    call("omlm_attn_fwd", _p(qn), _p(kvn), _p(table), _I(table.stride(0)), _p(key_mask), _p(out), _p(lse2),
+         _I(B), _I(N), _I(heads), _F(scale), _stream())
+
+
+def attn_bwd(qn, kvn, d_o, o, lse2, table, key_mask, dsum_scratch, dqn, dkvn, dtable, B, N, heads, scale=8.0):
+    call("omlm_attn_bwd", _p(qn), _p(kvn), _p(d_o), _p(o), _p(lse2), _p(table), _I(table.stride(0)), _p(key_mask),
+         _p(dsum_scratch), _p(dqn), _p(dkvn), _p(dtable), _I(B), _I(N), _I(heads), _F(scale), _stream())
+
+
+def ffn_mid_fwd(u, conv_w, gamma, hn, stats, B, N, F, Fp, drop_p=0.0, seed=None, layer=0):
+    call("omlm_ffn_mid_fwd", _p(u), _p(conv_w), _p(gamma), _p(hn), _p(stats), _I(B), _I(N), _I(F), _I(Fp),
+         _F(drop_p), _p(seed), _I(layer), _stream())
+
+
+def ffn_mid_bwd(dhn, u, stats, conv_w, gamma, dy_scratch, du, dgamma, dconv_w, B, N, F, Fp, drop_p=0.0, seed=None, layer=0):
+    call("omlm_ffn_mid_bwd", _p(dhn), _p(u), _p(stats), _p(conv_w), _p(gamma), _p(dy_scratch), _p(du), _p(dgamma),
+         _p(dconv_w), _I(B), _I(N), _I(F), _I(Fp), _F(drop_p), _p(seed), _I(layer), _stream())
+
+
+def cross_entropy(logits, labels, C, loss_acc, *, grad_scale=0.0, dlogits=None, ignore_index=-100, label_stride=1, rows=None):
+    rows = logits.shape[0] if rows is None else rows
+    call("omlm_cross_entropy", _p(logits), _L(logits.stride(0)), _p(labels), _I(label_stride), _I(rows), _I(C),
+         _I(ignore_index), _F(grad_scale), _p(dlogits), _L(dlogits.stride(0) if dlogits is not None else 0),
+         _I(dlogits.shape[1] if dlogits is not None else 0), _p(loss_acc), _stream())
+
+
+def grad_sumsq(g, acc, prescale=1.0):
+    call("omlm_grad_sumsq", _p(g), _L(g.numel()), _F(prescale), _p(acc), _stream())
+
+
+def adamw_step(p, g, m, v, n_decay, hyper, sumsq):
+    call("omlm_adamw_step", _p(p), _p(g), _p(m), _p(v), _L(p.numel()), _L(n_decay), _p(hyper), _p(sumsq), _stream())
+
+
+def pack(src, src_ld, rows_valid, cols_valid, dst, rows_p, cols_p, split_dst=0, split_src=0):
+    call("omlm_pack", _p(src), _L(src_ld), _I(rows_valid), _I(cols_valid), _p(dst), _I(int(dst.dtype == torch.float32)),
+         _L(cols_p if dst.dim() == 1 else dst.stride(0)), _I(rows_p), _I(cols_p), _I(split_dst), _I(split_src), _stream())
+
+
+def unpack_add(packed, rows_p, cols_p, dst, dst_ld, rows_valid, cols_valid, split_dst=0, split_src=0):
+    call("omlm_unpack_add", _p(packed), _L(cols_p if packed.dim() == 1 else packed.stride(0)), _I(rows_p), _I(cols_p),
+         _p(dst), _L(dst_ld), _I(rows_valid), _I(cols_valid), _I(split_dst), _I(split_src), _stream())

@@ -72,10 +72,10 @@ int omlm_embed_scatter_add(float* dtable, const int* src_row, const float* dx, i
 int omlm_layernorm_fwd(const float* x, const float* gamma, void* y_bf16, void* xraw_bf16, float* stats,
                        const int* dest_row, int M, int D, void* stream);
 /* dx = [dres] + [draw] + LN-backward(dy);  dgamma += sum_rows dy * xhat.  dy row for x row m is
- * src_row[m] when given (-1: no gradient). */
+ * src_row[m] when given (-1: no gradient).  dx_bf16 (optional): bf16 copy of dx for the next GEMMs. */
 int omlm_layernorm_bwd(const void* dy_bf16, const float* x, const float* stats, const float* gamma,
                        const float* dres, const void* draw_bf16, const int* src_row, float* dx,
-                       float* dgamma, int M, int D, void* stream);
+                       void* dx_bf16, float* dgamma, int M, int D, void* stream);
 /* l2norm * learned scale on queries / keys (transformer.py:269-271, utils.py:68-69).
  * q_raw [M, heads*64], kv_raw [M,128] (k | v) -> qn, kvn (k normalised, v copied). */
 int omlm_qk_l2norm_fwd(const void* q_raw, const void* kv_raw, const float* q_scale, const float* k_scale,

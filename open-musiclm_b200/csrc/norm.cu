@@ -75,7 +75,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
                      const float2* __restrict__ stats, const float* __restrict__ gamma,
                      const float* __restrict__ dres, const __nv_bfloat16* __restrict__ draw,
                      const int* __restrict__ src_row, float* __restrict__ dx,
-                     float* __restrict__ dgamma, int M, int D, int rows_per_block) {
+                     __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, int M, int D,
+                     int rows_per_block) {
   __shared__ float sdg[NCHUNK * 128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < NCHUNK * 128; i += kNormThreads) sdg[i] = 0.f;
@@ -130,6 +131,12 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
           o.x += r01.x; o.y += r01.y; o.z += r23.x; o.w += r23.y;
         }
         *reinterpret_cast<float4*>(dx + static_cast<long long>(row) * D + col) = o;
+        if (dx_bf16 != nullptr) {
+          uint2 ob;
+          ob.x = pack_bf16x2(o.x, o.y);
+          ob.y = pack_bf16x2(o.z, o.w);
+          *reinterpret_cast<uint2*>(dx_bf16 + static_cast<long long>(row) * D + col) = ob;
+        }
       }
     }
   }
@@ -305,14 +312,14 @@ static int launch_ln_fwd(const float* x, const float* gamma, __nv_bfloat16* y, _
 template <int NCHUNK>
 static int launch_ln_bwd(const __nv_bfloat16* dy, const float* x, const float2* stats, const float* gamma,
                          const float* dres, const __nv_bfloat16* draw, const int* src_row, float* dx,
-                         float* dgamma, int M, int D, cudaStream_t st) {
+                         __nv_bfloat16* dx_bf16, float* dgamma, int M, int D, cudaStream_t st) {
   // ~4 blocks per SM; each block walks a contiguous slab of rows and flushes dgamma once.
   int blocks = num_sms() * 4;
   int rows_per_block = (M + blocks - 1) / blocks;
   if (rows_per_block < 8) rows_per_block = 8;
   blocks = (M + rows_per_block - 1) / rows_per_block;
   layernorm_bwd_kernel<NCHUNK><<<blocks, kNormThreads, 0, st>>>(dy, x, stats, gamma, dres, draw, src_row, dx,
-                                                               dgamma, M, D, rows_per_block);
+                                                               dx_bf16, dgamma, M, D, rows_per_block);
   OMLM_LAUNCH_CHECK();
   return 0;
 }
@@ -339,19 +346,20 @@ int omlm_layernorm_fwd(const float* x, const float* gamma, void* y_bf16, void* x
 
 int omlm_layernorm_bwd(const void* dy_bf16, const float* x, const float* stats, const float* gamma,
                        const float* dres, const void* draw_bf16, const int* src_row, float* dx,
-                       float* dgamma, int M, int D, void* stream) {
+                       void* dx_bf16, float* dgamma, int M, int D, void* stream) {
   using namespace omlm;
   OMLM_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0 && D <= 2048, "layernorm_bwd: unsupported shape %d x %d", M, D);
   auto st = reinterpret_cast<cudaStream_t>(stream);
   auto dy = reinterpret_cast<const __nv_bfloat16*>(dy_bf16);
   auto dr = reinterpret_cast<const __nv_bfloat16*>(draw_bf16);
   auto s2 = reinterpret_cast<const float2*>(stats);
+  auto dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
   const int nchunk = (D + 127) / 128;
-  if (nchunk <= 1) return launch_ln_bwd<1>(dy, x, s2, gamma, dres, dr, src_row, dx, dgamma, M, D, st);
-  if (nchunk <= 2) return launch_ln_bwd<2>(dy, x, s2, gamma, dres, dr, src_row, dx, dgamma, M, D, st);
-  if (nchunk <= 4) return launch_ln_bwd<4>(dy, x, s2, gamma, dres, dr, src_row, dx, dgamma, M, D, st);
-  if (nchunk <= 8) return launch_ln_bwd<8>(dy, x, s2, gamma, dres, dr, src_row, dx, dgamma, M, D, st);
-  return launch_ln_bwd<16>(dy, x, s2, gamma, dres, dr, src_row, dx, dgamma, M, D, st);
+  if (nchunk <= 1) return launch_ln_bwd<1>(dy, x, s2, gamma, dres, dr, src_row, dx, dxb, dgamma, M, D, st);
+  if (nchunk <= 2) return launch_ln_bwd<2>(dy, x, s2, gamma, dres, dr, src_row, dx, dxb, dgamma, M, D, st);
+  if (nchunk <= 4) return launch_ln_bwd<4>(dy, x, s2, gamma, dres, dr, src_row, dx, dxb, dgamma, M, D, st);
+  if (nchunk <= 8) return launch_ln_bwd<8>(dy, x, s2, gamma, dres, dr, src_row, dx, dxb, dgamma, M, D, st);
+  return launch_ln_bwd<16>(dy, x, s2, gamma, dres, dr, src_row, dx, dxb, dgamma, M, D, st);
 }
 
 int omlm_qk_l2norm_fwd(const void* q_raw, const void* kv_raw, const float* q_scale, const float* k_scale,

@@ -1,0 +1,440 @@
+"""Host-side engine of the hot path: owns the flat parameter arena, the packed bf16 compute weights and
+the activation workspaces, and sequences the libomlm_b200 kernels for forward, backward and the
+optimiser step.  PyTorch supplies device memory and streams only; every arithmetic op is a call into
+the C ABI (open_musiclm_b200.lib).
+
+HBM layout
+  arena_p / arena_g / adam_m / adam_v : one fp32 buffer each, parameters ordered
+        [embeddings | logit heads | layer matrices | rel-pos MLP matrices]   <- weight-decayed (ndim >= 2)
+        [start tokens | gammas, scales, MLP biases]                          <- not decayed
+        every nn.Parameter of the module is a view into arena_p (and its .grad into arena_g).
+  packed weights (bf16, refreshed after every parameter update):
+        wq [h*64, d], wkv [128, d], wo [d, h*64], w1 [2*Fp, d] (value rows | gate rows, zero padded),
+        w2 [d, Fp], logit heads [q, Cp, d];  conv taps fp32 [2*Fp, 3], inner gamma fp32 [Fp].
+  activations: residual stream fp32 [M, d]; GEMM operands bf16; attention statistics fp32.
+"""
+import math
+from typing import List, Optional
+
+import torch
+
+from . import lib
+
+CE_IGNORE = -100
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class _Plan:
+    """Static shape bookkeeping for one (batch, sequence lengths) configuration."""
+
+    def __init__(self, eng: "Engine", B: int, n_tok: List[int], device):
+        self.B = B
+        self.n_tok = list(n_tok)
+        S = len(n_tok)
+        self.N = sum(n + 1 for n in n_tok)
+        self.M = B * self.N
+        self.pos0 = list(itertools_accumulate([0] + [n + 1 for n in n_tok[:-1]]))
+        # logits positions per sequence (open_musiclm.py:149-156)
+        self.n_out = [n_tok[s] if s < S - 1 else n_tok[s] + 1 for s in range(S)]
+        # head groups: (s, qi) -> rows ordered (b, t), position p = qi + q*t
+        self.groups = []
+        dest = torch.full((B, self.N), -1, dtype=torch.int32)
+        base = 0
+        self.seq_row_index = []   # per sequence: [B, n_out] -> row in the permuted buffers
+        for s in range(S):
+            q = eng.seqs[s].num_quantizers
+            idx = torch.empty(B, self.n_out[s], dtype=torch.int64)
+            for qi in range(min(q, self.n_out[s])):
+                cnt = (self.n_out[s] - qi + q - 1) // q
+                rows = base + torch.arange(B)[:, None] * cnt + torch.arange(cnt)[None, :]
+                pos = qi + q * torch.arange(cnt)
+                dest[:, self.pos0[s] + pos] = rows.to(torch.int32)
+                idx[:, pos] = rows
+                self.groups.append((s, qi, cnt, base))
+                base += B * cnt
+            self.seq_row_index.append(idx.to(device))
+        self.rows_total = base
+        self.dest_row = dest.reshape(-1).to(device)
+
+
+def itertools_accumulate(xs):
+    t = 0
+    out = []
+    for x in xs:
+        t += x
+        out.append(t)
+    return out
+
+
+class Engine:
+    def __init__(self, module):
+        lib.load()
+        self.m = module
+        dev = module.device
+        if dev.type != "cuda":
+            raise lib.OmlmError("open_musiclm_b200 needs a CUDA (sm_100a) device: move the module with .to('cuda') "
+                                "before calling it - there is no CPU fallback")
+        lib.device_check()
+        self.dev = dev
+        self.seqs = module.token_sequences
+        self.d, self.L, self.h = module.dim, module.depth, module.heads
+        self.HD = self.h * 64
+        self.F = int(self.d * 2 * 4 / 3)
+        self.Fp = _round_up(self.F, 64)
+        self.Hr = self.d // 2                      # rel-pos MLP width
+        self.C = [s.codebook_size + 1 for s in self.seqs]
+        self.Cp = [_round_up(c, 64) for c in self.C]
+        self.drop_p = float(module.ff_dropout)
+        self.alpha = float(module.grad_shrink_alpha)
+        self._build_arena()
+        self._alloc_packed()
+        self._packed_version = None
+        self._plans = {}
+        self._ws = {}
+        self.seed = torch.zeros(1, dtype=torch.int64, device=dev)      # dropout / forgetful-mask seed (device resident)
+        self.step_count = 0
+        self.adam_m = None
+        self.adam_v = None
+        self.loss_acc = torch.zeros(2, device=dev)
+        self.sumsq = torch.zeros(1, device=dev, dtype=torch.float64)
+
+    # ------------------------------------------------------------------------------------------ arena
+    def _build_arena(self):
+        named = [(n, p) for n, p in self.m.named_parameters()]
+        emb = [(n, p) for n, p in named if n.startswith("embeddings.")]
+        start = [(n, p) for n, p in named if n.startswith("start_tokens.")]
+        decay = emb + [(n, p) for n, p in named if p.ndim >= 2 and not n.startswith("embeddings.")]
+        nodecay = start + [(n, p) for n, p in named if p.ndim < 2 and not n.startswith("start_tokens.")]
+        off, layout = 0, {}
+        for n, p in decay:
+            layout[n] = off
+            off = _round_up(off + p.numel(), 64)
+        self.n_decay = off
+        emb_off = layout[emb[0][0]]
+        # start tokens are addressed as rows of the embedding "table": keep them row-aligned to it
+        off = emb_off + _round_up(off - emb_off, self.d)
+        self.n_decay = off
+        for n, p in nodecay:
+            layout[n] = off
+            off = _round_up(off + p.numel(), 64)
+        self.n_params_arena = off
+        self.layout = layout
+        arena_p = torch.zeros(off, device=self.dev, dtype=torch.float32)
+        arena_g = torch.zeros(off, device=self.dev, dtype=torch.float32)
+        self.pview, self.gview = {}, {}
+        for n, p in named:
+            o = layout[n]
+            v = arena_p[o:o + p.numel()].view(p.shape)
+            v.copy_(p.data)
+            p.data = v
+            g = arena_g[o:o + p.numel()].view(p.shape)
+            p.grad = g
+            self.pview[n], self.gview[n] = v, g
+        self.arena_p, self.arena_g = arena_p, arena_g
+        # embedding table = [embeddings.0 | embeddings.1 | ... ] rows of d floats; start tokens further down
+        self.emb_off = emb_off
+        self.emb_row_base, r = [], 0
+        for n, p in emb:
+            assert (layout[n] - emb_off) % self.d == 0
+            self.emb_row_base.append((layout[n] - emb_off) // self.d)
+        self.start_row = [(layout[n] - emb_off) // self.d for n, _ in start]
+        self.table = arena_p[emb_off:]
+        self.dtable_emb = arena_g[emb_off:]
+        self._param_list = [p for _, p in named]
+
+    def params_version(self):
+        return sum(p._version for p in self._param_list)
+
+    def _alloc_packed(self):
+        dev, bf = self.dev, torch.bfloat16
+        d, HD, Fp = self.d, self.HD, self.Fp
+        self.pk = []
+        for _ in range(self.L):
+            self.pk.append(dict(
+                wq=torch.empty(HD, d, device=dev, dtype=bf), wkv=torch.empty(128, d, device=dev, dtype=bf),
+                wo=torch.empty(d, HD, device=dev, dtype=bf), w1=torch.empty(2 * Fp, d, device=dev, dtype=bf),
+                w2=torch.empty(d, Fp, device=dev, dtype=bf), conv=torch.empty(2 * Fp, 3, device=dev),
+                gin=torch.empty(Fp, device=dev)))
+        self.pk_logit = [torch.empty(s.num_quantizers, cp, d, device=dev, dtype=bf) for s, cp in zip(self.seqs, self.Cp)]
+
+    def refresh_packed(self, force=False):
+        ver = self.params_version()
+        if not force and ver == self._packed_version:
+            return
+        d, HD, F, Fp = self.d, self.HD, self.F, self.Fp
+        pv = self.pview
+        for l, pk in enumerate(self.pk):
+            p = f"transformer.layers.{l}."
+            lib.pack(pv[p + "0.to_q.weight"], d, HD, d, pk["wq"], HD, d)
+            lib.pack(pv[p + "0.to_kv.weight"], d, 128, d, pk["wkv"], 128, d)
+            lib.pack(pv[p + "0.to_out.0.weight"], HD, d, HD, pk["wo"], d, HD)
+            lib.pack(pv[p + "2.1.weight"], d, 2 * F, d, pk["w1"], 2 * Fp, d, split_dst=Fp, split_src=F)
+            lib.pack(pv[p + "2.6.weight"], F, d, F, pk["w2"], d, Fp)
+            lib.pack(pv[p + "2.2.ds_conv.weight"], 3, 2 * F, 3, pk["conv"], 2 * Fp, 3, split_dst=Fp, split_src=F)
+            lib.pack(pv[p + "2.4.gamma"], F, 1, F, pk["gin"], 1, Fp)
+        for s, seq in enumerate(self.seqs):
+            # [q, C, d] -> [q, Cp, d]: every head padded with zero rows
+            lib.pack(pv[f"logit_weights.{s}"], d, seq.num_quantizers * self.C[s], d, self.pk_logit[s].view(-1, d),
+                     seq.num_quantizers * self.Cp[s], d, split_dst=self.Cp[s], split_src=self.C[s])
+        self._packed_version = ver
+
+    # ------------------------------------------------------------------------------------------ plans / workspaces
+    def plan(self, B, n_tok) -> _Plan:
+        key = (B, tuple(n_tok))
+        if key not in self._plans:
+            self._plans[key] = _Plan(self, B, n_tok, self.dev)
+        return self._plans[key]
+
+    def workspace(self, pl: _Plan, train: bool):
+        key = (pl.B, tuple(pl.n_tok), train)
+        if key in self._ws:
+            return self._ws[key]
+        dev, bf, f32 = self.dev, torch.bfloat16, torch.float32
+        M, d, HD, Fp, h = pl.M, self.d, self.HD, self.Fp, self.h
+        E = lambda *shape, dt=bf: torch.empty(*shape, device=dev, dtype=dt)
+        nl = self.L if train else 1
+        ws = dict(
+            x=[E(M, d, dt=f32) for _ in range(2 * nl + 1)],       # residual stream snapshots: x_l, x_mid_l, ..., x_L
+            xn=[E(M, d) for _ in range(nl)], xraw=[E(M, d) for _ in range(nl)], st_a=[E(M, 2, dt=f32) for _ in range(nl)],
+            q_raw=[E(M, HD) for _ in range(nl)], kv_raw=[E(M, 128) for _ in range(nl)],
+            qn=[E(M, HD) for _ in range(nl)], kvn=[E(M, 128) for _ in range(nl)],
+            o=[E(M, HD) for _ in range(nl)], lse=[E(M * h, dt=f32) for _ in range(nl)],
+            xn2=[E(M, d) for _ in range(nl)], st_f=[E(M, 2, dt=f32) for _ in range(nl)],
+            u=[E(M, 2 * Fp) for _ in range(nl)], hn=[E(M, Fp) for _ in range(nl)], st_i=[E(M, 2, dt=f32) for _ in range(nl)],
+            xf=E(max(pl.rows_total, 1), d), st_o=E(M, 2, dt=f32),
+            logits=[E(max(pl.B * c, 1), self.Cp[s], dt=f32) for (s, qi, c, b0) in pl.groups],
+            # rel-pos MLP
+            rp_in=E(pl.N, 1, dt=f32), rp_z=[E(pl.N, self.Hr, dt=f32) for _ in range(3)],
+            rp_a=[E(pl.N, self.Hr, dt=f32) for _ in range(3)], table=E(h, pl.N, dt=f32),
+        )
+        lib.arange_f32(ws["rp_in"])
+        if train:
+            ws.update(
+                dlogits=[E(max(pl.B * c, 1), self.Cp[s]) for (s, qi, c, b0) in pl.groups],
+                dxf=E(max(pl.rows_total, 1), d), dx=[E(M, d, dt=f32) for _ in range(2)], dx_bf=E(M, d),
+                dhn=E(M, Fp), dy=E(M, 2 * Fp), du=E(M, 2 * Fp), dxn=E(M, d), dxraw=E(M, d),
+                d_o=E(M, HD), dqn=E(M, HD, dt=f32), dkvn=E(M, 128, dt=f32), dsum=E(M * h, dt=f32),
+                dq_raw=E(M, HD), dkv_raw=E(M, 128), dtable=E(h, pl.N, dt=f32),
+                dgin=E(Fp, dt=f32), dconv=E(2 * Fp, 3, dt=f32),
+                rp_d0=E(pl.N, self.Hr, dt=f32), rp_d1=E(pl.N, self.Hr, dt=f32),
+            )
+        self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------------------------------ forward
+    @staticmethod
+    def _bn(N):
+        return 256 if N % 256 == 0 or N >= 2048 else 128
+
+    def _relpos_table(self, ws, N):
+        """RelativePositionBias MLP on the causal distances 0..N-1 -> table[h, N] (transformer.py:55-67)."""
+        pv, Hr, h = self.pview, self.Hr, self.h
+        pre = "transformer.rel_pos_bias.net."
+        a = ws["rp_in"]
+        K = 1
+        for j in range(3):
+            W, b = pv[f"{pre}{j}.0.weight"], pv[f"{pre}{j}.0.bias"]
+            lib.sgemm_small(a, (K, 1), W, (1, K), ws["rp_a"][j], (Hr, 1), N, Hr, K, Z=ws["rp_z"][j], bias=b, act=1)
+            a, K = ws["rp_a"][j], Hr
+        lib.sgemm_small(a, (Hr, 1), pv[pre + "3.weight"], (1, Hr), ws["table"], (1, N), N, h, Hr, bias=pv[pre + "3.bias"])
+
+    def forward_core(self, pl: _Plan, ws, src_row, key_mask, train: bool, groups_wanted=None, drop: bool = False):
+        """Runs embeddings -> depth x (attention, conv-FFN) -> final LN -> logit heads.  Activations stay in `ws`."""
+        self.refresh_packed()
+        B, N, M, d, h, HD, F, Fp = pl.B, pl.N, pl.M, self.d, self.h, self.HD, self.F, self.Fp
+        pv = self.pview
+        x = ws["x"]
+        lib.embed_gather(self.table, src_row, x[0])
+        self._relpos_table(ws, N)
+        drop_p = self.drop_p if drop else 0.0
+        for l in range(self.L):
+            i = l if train else 0
+            xa, xm, xo = (x[2 * l], x[2 * l + 1], x[2 * l + 2]) if train else (x[0], x[1], x[0])
+            p, pk = f"transformer.layers.{l}.", self.pk[l]
+            lib.layernorm_fwd(xa, pv[p + "0.norm.gamma"], ws["xn"][i], ws["xraw"][i], ws["st_a"][i])
+            lib.gemm(ws["xn"][i], pk["wq"], ws["q_raw"][i], block_n=self._bn(HD))
+            lib.gemm(ws["xraw"][i], pk["wkv"], ws["kv_raw"][i], block_n=128)
+            lib.qk_l2norm_fwd(ws["q_raw"][i], ws["kv_raw"][i], pv[p + "0.q_scale"], pv[p + "0.k_scale"], ws["qn"][i], ws["kvn"][i], h)
+            lib.attn_fwd(ws["qn"][i], ws["kvn"][i], ws["table"], key_mask, ws["o"][i], ws["lse"][i], B, N, h)
+            lib.gemm(ws["o"][i], pk["wo"], xm, addend=xa, block_n=128)
+            lib.layernorm_fwd(xm, pv[p + "2.0.gamma"], ws["xn2"][i], None, ws["st_f"][i])
+            lib.gemm(ws["xn2"][i], pk["w1"], ws["u"][i], block_n=256)
+            lib.ffn_mid_fwd(ws["u"][i], pk["conv"], pk["gin"], ws["hn"][i], ws["st_i"][i], B, N, F, Fp, drop_p, self.seed, l)
+            lib.gemm(ws["hn"][i], pk["w2"], xo, addend=xm, block_n=128)
+        x_last = x[2 * self.L] if train else x[0]
+        lib.layernorm_fwd(x_last, pv["transformer.norm.gamma"], ws["xf"], None, ws["st_o"], pl.dest_row)
+        for gi, (s, qi, cnt, base) in enumerate(pl.groups):
+            if groups_wanted is not None and s not in groups_wanted:
+                continue
+            rows = B * cnt
+            lib.gemm(ws["xf"][base:base + rows], self.pk_logit[s][qi], ws["logits"][gi], block_n=128)
+
+    # ------------------------------------------------------------------------------------------ backward
+    def _splits(self, m, n, k, bn=128):
+        tiles = ((m + 127) // 128) * ((n + bn - 1) // bn)
+        kb = (k + 63) // 64
+        s = max(1, min((2 * 148 + tiles - 1) // tiles, kb // 4 if kb >= 4 else 1))
+        return s
+
+    def _wgrad(self, dy, x, gout, m, n, **kw):
+        """gout[m, n] += dy[rows, m]^T x[rows, n]   (both operands MN-major, fp32 accumulate into the grad arena)."""
+        k = dy.shape[0]
+        s = self._splits(m, n, k)
+        if s > 1:
+            lib.gemm(dy, x, gout, a_mn=True, b_mn=True, M=m, N=n, K=k, splits=s, **kw)
+        else:
+            lib.gemm(dy, x, gout, a_mn=True, b_mn=True, M=m, N=n, K=k, addend=gout, **kw)
+
+    def backward_core(self, pl: _Plan, ws, src_row, key_mask, groups_with_grad, drop: bool = False):
+        """Consumes ws['dlogits'] (bf16, permuted rows) and accumulates every parameter gradient into arena_g."""
+        B, N, M, d, h, HD, F, Fp = pl.B, pl.N, pl.M, self.d, self.h, self.HD, self.F, self.Fp
+        pv, gv = self.pview, self.gview
+        x = ws["x"]
+        drop_p = self.drop_p if drop else 0.0
+        # ---- logit heads
+        ws["dxf"].zero_()
+        for gi, (s, qi, cnt, base) in enumerate(pl.groups):
+            if s not in groups_with_grad:
+                continue
+            rows = B * cnt
+            dl = ws["dlogits"][gi]
+            lib.gemm(dl, self.pk_logit[s][qi], ws["dxf"][base:base + rows], b_mn=True, M=rows, N=d, K=self.Cp[s], block_n=128)
+            self._wgrad(dl, ws["xf"][base:base + rows], gv[f"logit_weights.{s}"][qi], self.Cp[s], d, row_split=self.Cp[s], row_valid=self.C[s])
+        dxa, dxb = ws["dx"]
+        lib.layernorm_bwd(ws["dxf"], x[2 * self.L], ws["st_o"], pv["transformer.norm.gamma"], dxa, gv["transformer.norm.gamma"],
+                          src_row=pl.dest_row, dx_bf16=ws["dx_bf"])
+        ws["dtable"].zero_()
+        for l in reversed(range(self.L)):
+            p, pk = f"transformer.layers.{l}.", self.pk[l]
+            xa, xm = x[2 * l], x[2 * l + 1]
+            # ---- conv feed-forward
+            lib.gemm(ws["dx_bf"], pk["w2"], ws["dhn"], b_mn=True, M=M, N=Fp, K=d, block_n=self._bn(Fp))
+            self._wgrad(ws["dx_bf"], ws["hn"][l], gv[p + "2.6.weight"], d, Fp, n_valid=F)
+            ws["dgin"].zero_(); ws["dconv"].zero_()
+            lib.ffn_mid_bwd(ws["dhn"], ws["u"][l], ws["st_i"][l], pk["conv"], pk["gin"], ws["dy"], ws["du"], ws["dgin"], ws["dconv"],
+                            B, N, F, Fp, drop_p, self.seed, l)
+            lib.unpack_add(ws["dgin"], 1, Fp, gv[p + "2.4.gamma"], F, 1, F)
+            lib.unpack_add(ws["dconv"], 2 * Fp, 3, gv[p + "2.2.ds_conv.weight"], 3, 2 * F, 3, split_dst=Fp, split_src=F)
+            lib.gemm(ws["du"], pk["w1"], ws["dxn"], b_mn=True, M=M, N=d, K=2 * Fp, block_n=128)
+            self._wgrad(ws["du"], ws["xn2"][l], gv[p + "2.1.weight"], 2 * Fp, d, row_split=Fp, row_valid=F)
+            lib.layernorm_bwd(ws["dxn"], xm, ws["st_f"][l], pv[p + "2.0.gamma"], dxb, gv[p + "2.0.gamma"], dres=dxa, dx_bf16=ws["dx_bf"])
+            # ---- attention
+            lib.gemm(ws["dx_bf"], pk["wo"], ws["d_o"], b_mn=True, M=M, N=HD, K=d, block_n=self._bn(HD))
+            self._wgrad(ws["dx_bf"], ws["o"][l], gv[p + "0.to_out.0.weight"], d, HD)
+            ws["dqn"].zero_(); ws["dkvn"].zero_()
+            lib.attn_bwd(ws["qn"][l], ws["kvn"][l], ws["d_o"], ws["o"][l], ws["lse"][l], ws["table"], key_mask, ws["dsum"],
+                         ws["dqn"], ws["dkvn"], ws["dtable"], B, N, h)
+            lib.qk_l2norm_bwd(ws["dqn"], ws["dkvn"], ws["q_raw"][l], ws["kv_raw"][l], pv[p + "0.q_scale"], pv[p + "0.k_scale"],
+                              ws["dq_raw"], ws["dkv_raw"], gv[p + "0.q_scale"], gv[p + "0.k_scale"], h)
+            lib.gemm(ws["dq_raw"], pk["wq"], ws["dxn"], b_mn=True, M=M, N=d, K=HD, block_n=128)
+            lib.gemm(ws["dkv_raw"], pk["wkv"], ws["dxraw"], b_mn=True, M=M, N=d, K=128, block_n=128)
+            self._wgrad(ws["dq_raw"], ws["xn"][l], gv[p + "0.to_q.weight"], HD, d)
+            self._wgrad(ws["dkv_raw"], ws["xraw"][l], gv[p + "0.to_kv.weight"], 128, d)
+            lib.layernorm_bwd(ws["dxn"], xa, ws["st_a"][l], pv[p + "0.norm.gamma"], dxa, gv[p + "0.norm.gamma"], dres=dxb, draw=ws["dxraw"],
+                              dx_bf16=ws["dx_bf"])
+        # ---- embeddings + start tokens (grad_shrink: utils.py:60-61)
+        lib.embed_scatter_add(self.dtable_emb, src_row, dxa, self.alpha)
+        self._relpos_backward(ws, N)
+
+    def _relpos_backward(self, ws, N):
+        pv, gv, Hr, h = self.pview, self.gview, self.Hr, self.h
+        pre = "transformer.rel_pos_bias.net."
+        dT = ws["dtable"]                                   # [h, N]: dY[n, hh] = dT[hh, n]
+        a3 = ws["rp_a"][2]
+        lib.sgemm_small(dT, (N, 1), a3, (Hr, 1), gv[pre + "3.weight"], (Hr, 1), h, Hr, N, accumulate=True)      # dW4 = dY^T a3
+        lib.colsum(dT, 1, N, gv[pre + "3.bias"], N, h, accumulate=True)
+        d_cur, d_nxt = ws["rp_d0"], ws["rp_d1"]
+        lib.sgemm_small(dT, (1, N), pv[pre + "3.weight"], (Hr, 1), d_cur, (Hr, 1), N, Hr, h)                      # da3 = dY W4
+        for j in (2, 1, 0):
+            lib.silu_bwd(d_cur, ws["rp_z"][j], d_cur)                                                             # dz_j
+            a_prev, K = (ws["rp_a"][j - 1], Hr) if j > 0 else (ws["rp_in"], 1)
+            lib.sgemm_small(d_cur, (1, Hr), a_prev, (K, 1), gv[f"{pre}{j}.0.weight"], (K, 1), Hr, K, N, accumulate=True)
+            lib.colsum(d_cur, Hr, 1, gv[f"{pre}{j}.0.bias"], N, Hr, accumulate=True)
+            if j > 0:
+                lib.sgemm_small(d_cur, (Hr, 1), pv[f"{pre}{j}.0.weight"], (Hr, 1), d_nxt, (Hr, 1), N, Hr, Hr)     # da_{j-1} = dz_j W_j
+                d_cur, d_nxt = d_nxt, d_cur
+
+    # ------------------------------------------------------------------------------------------ reference-API path
+    def api_forward(self, all_token_ids, self_attn_mask, only_final):
+        ids = [t.reshape(t.shape[0], -1).to(self.dev, torch.int64).contiguous() for t in all_token_ids]
+        assert len(ids) == len(self.seqs)
+        B = ids[0].shape[0]
+        mask_in = None
+        if self_attn_mask is not None:
+            mask_in = self_attn_mask.to(self.dev).to(torch.uint8).contiguous()
+        _, src_row, key_mask, _, n_tok = lib.token_plan(
+            ids, [s.codebook_size for s in self.seqs], [s.num_quantizers for s in self.seqs], self.emb_row_base,
+            self.start_row, append_eos=False, drop_last=False, mask_cond=False, mask_in=mask_in, want_labels=False)
+        pl = self.plan(B, n_tok)
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self._param_list)
+        wanted = {len(self.seqs) - 1} if only_final else set(range(len(self.seqs)))
+        drop = self.m.training and self.drop_p > 0
+        if drop:
+            self.seed += 1
+        outs = _ApiFunction.apply(self, pl, src_row, key_mask, need_grad, wanted, drop, *self._param_list)
+        res, k = [], 0
+        for s in range(len(self.seqs)):
+            if s in wanted:
+                res.append(outs[k]); k += 1
+            else:
+                res.append(None)
+        return res
+
+    def gather_logits(self, pl, ws, s):
+        """Permuted group buffers -> [B, n_out, C] fp32 (re-layout only)."""
+        parts = [ws["logits"][gi][:, :self.C[s]] for gi, g in enumerate(pl.groups) if g[0] == s]
+        allrows = torch.cat(parts, 0)
+        first = min(g[3] for g in pl.groups if g[0] == s)
+        return allrows[(pl.seq_row_index[s] - first).reshape(-1)].view(pl.B, pl.n_out[s], self.C[s])
+
+    def scatter_dlogits(self, pl, ws, s, grad):
+        """[B, n_out, C] fp32 gradient -> permuted bf16 dlogits buffers (re-layout + cast only)."""
+        first = min(g[3] for g in pl.groups if g[0] == s)
+        total = sum(pl.B * g[2] for g in pl.groups if g[0] == s)
+        buf = torch.zeros(total, self.Cp[s], device=self.dev, dtype=torch.bfloat16)
+        buf[(pl.seq_row_index[s] - first).reshape(-1), :self.C[s]] = grad.reshape(-1, self.C[s]).to(torch.bfloat16)
+        off = 0
+        for gi, g in enumerate(pl.groups):
+            if g[0] == s:
+                n = pl.B * g[2]
+                ws["dlogits"][gi].copy_(buf[off:off + n]); off += n
+
+
+class _ApiFunction(torch.autograd.Function):
+    """One autograd node for the whole TokenConditionedTransformer.forward: libomlm_b200 forward in
+    forward(), libomlm_b200 backward in backward(); gradients are returned per parameter."""
+
+    @staticmethod
+    def forward(ctx, eng: Engine, pl, src_row, key_mask, need_grad, wanted, drop, *params):
+        ws = eng.workspace(pl, need_grad)
+        eng.forward_core(pl, ws, src_row, key_mask, need_grad, wanted, drop)
+        ctx.eng, ctx.pl, ctx.src_row, ctx.key_mask, ctx.wanted, ctx.drop = eng, pl, src_row, key_mask, sorted(wanted), drop
+        ctx.need_grad = need_grad
+        outs = tuple(eng.gather_logits(pl, ws, s) for s in sorted(wanted))
+        return outs
+
+    @staticmethod
+    def backward(ctx, *grads):
+        eng, pl = ctx.eng, ctx.pl
+        if not ctx.need_grad:
+            raise RuntimeError("forward ran without gradient bookkeeping")
+        ws = eng.workspace(pl, True)
+        with_grad = set()
+        for s, g in zip(ctx.wanted, grads):
+            if g is not None:
+                eng.scatter_dlogits(pl, ws, s, g)
+                with_grad.add(s)
+        # gradients are produced in a scratch copy of the arena so that autograd can accumulate them itself
+        saved = eng.arena_g.clone()
+        eng.arena_g.zero_()
+        eng.backward_core(pl, ws, ctx.src_row, ctx.key_mask, with_grad, ctx.drop)
+        fresh = eng.arena_g.clone()
+        eng.arena_g.copy_(saved)
+        outs = []
+        for n, p in eng.m.named_parameters():
+            o = eng.layout[n]
+            outs.append(fresh[o:o + p.numel()].view(p.shape))
+        return (None, None, None, None, None, None, None, *outs)

@@ -143,10 +143,10 @@ def layernorm_fwd(x, gamma, y, xraw=None, stats=None, dest_row=None):
     call("omlm_layernorm_fwd", _p(x), _p(gamma), _p(y), _p(xraw), _p(stats), _p(dest_row), _I(M), _I(D), _stream())
 
 
-def layernorm_bwd(dy, x, stats, gamma, dx, dgamma, dres=None, draw=None, src_row=None):
+def layernorm_bwd(dy, x, stats, gamma, dx, dgamma, dres=None, draw=None, src_row=None, dx_bf16=None):
     M, D = x.shape
     call("omlm_layernorm_bwd", _p(dy), _p(x), _p(stats), _p(gamma), _p(dres), _p(draw), _p(src_row), _p(dx),
-         _p(dgamma), _I(M), _I(D), _stream())
+         _p(dx_bf16), _p(dgamma), _I(M), _I(D), _stream())
 
 
 def qk_l2norm_fwd(q_raw, kv_raw, q_scale, k_scale, qn, kvn, heads):

@@ -1,0 +1,141 @@
+"""B200-native replacement of the SingleStageTrainer step loop (open_musiclm/trainer.py:415-452) on
+top of the engine: per micro-batch  wrapper pre-processing -> forward -> cross entropy -> backward
+(gradients accumulate in the flat fp32 arena), then ONE gradient all-reduce over NCCL, global-norm
+clip, AdamW and the LinearLR warm-up — every arithmetic step a libomlm_b200 kernel.
+
+Semantics kept from the reference:
+  * TokenConditionedTransformerWrapper.forward(return_loss=True) in training mode: eos append, labels,
+    key mask with zeroed conditioning ids, 15 % forgetful mask, FFN dropout (open_musiclm.py:328-410);
+    loss = sum_{w_s>0} CE_s * n_s * w_s / sum_{w_s>0} n_s (open_musiclm.py:391-410).
+  * loss / grad_accum_every per micro-batch (trainer.py:437-439); clip_grad_norm_(max_grad_norm);
+    AdamW(lr, betas (0.9, 0.99), eps 1e-8, wd on ndim>=2 params only) (optimizer.py:3-34);
+    LinearLR(start_factor 1e-7, total_iters lr_warmup) when lr_warmup > 0 (optimizer.py:36-40).
+  * DDP mean of gradients over ranks (trainer.py:154-155, 439) — here a single all-reduce(sum) of the
+    arena after the last micro-batch, the 1/world factor folded into the clip/AdamW kernel
+    (the reference all-reduces on every micro-batch; the reduced result is identical).
+"""
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import lib
+from .model import TokenConditionedTransformer
+
+
+class HotPathTrainer:
+    def __init__(self, transformer: TokenConditionedTransformer, *, cross_entropy_loss_weights: Optional[List[float]] = None,
+                 lr=3e-4, lr_warmup=0, wd=0., max_grad_norm=0.5, grad_accum_every=1, mask_prob=0.15,
+                 betas=(0.9, 0.99), eps=1e-8, pad_id=-1, seed=0, process_group=None):
+        self.transformer = transformer
+        self.eng = transformer.engine
+        eng = self.eng
+        S = len(eng.seqs)
+        self.ce_weights = list(cross_entropy_loss_weights) if cross_entropy_loss_weights is not None else [1.0] * S
+        assert len(self.ce_weights) == S
+        self.lr, self.lr_warmup, self.wd, self.max_grad_norm = lr, lr_warmup, wd, max_grad_norm
+        self.grad_accum_every = grad_accum_every
+        self.mask_prob = mask_prob
+        self.betas, self.eps, self.pad_id = betas, eps, pad_id
+        self.steps = 0
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(process_group) if self.world > 1 else 0
+        eng.seed.fill_(seed * 1000003 + self.rank * 7919 + 1)     # per-rank random streams (dropout / forgetful mask)
+        eng.adam_m = torch.zeros_like(eng.arena_p)
+        eng.adam_v = torch.zeros_like(eng.arena_p)
+        self.hyper_host = torch.zeros(9, dtype=torch.float32).pin_memory()
+        self.hyper = torch.zeros(9, dtype=torch.float32, device=eng.dev)
+        self.loss_buf = torch.zeros(grad_accum_every, device=eng.dev)
+        self._mask_draws = 0
+        eng.arena_g.zero_()
+
+    # -------------------------------------------------------------------------------------------
+    def _micro_batch(self, token_ids: Sequence[torch.Tensor], train: bool, slot: int, backward: bool):
+        eng = self.eng
+        dev = eng.dev
+        ids = [t.reshape(t.shape[0], -1).to(dev, torch.int64, non_blocking=True) for t in token_ids]
+        B = ids[0].shape[0]
+        S = len(eng.seqs)
+        # shapes are static per configuration: N is known before the plan kernel runs
+        n_tok = [t.shape[1] + 1 - (1 if s == S - 1 else 0) for s, t in enumerate(ids)]
+        pl = eng.plan(B, n_tok)
+        forget = None
+        if train and self.mask_prob > 0:
+            num_drop = min(int(pl.N * self.mask_prob), pl.N - 1)        # utils.py:53
+            self._mask_draws += 1
+            forget = lib.forgetful_mask(B, pl.N, num_drop, eng.seed, self._mask_draws, dev)
+        _, src_row, key_mask, labels, _ = lib.token_plan(
+            ids, [s.codebook_size for s in eng.seqs], [s.num_quantizers for s in eng.seqs], eng.emb_row_base,
+            eng.start_row, append_eos=True, drop_last=True, mask_cond=True, pad_id=self.pad_id, forget_keep=forget)
+        ws = eng.workspace(pl, backward)
+        weighted = {s for s in range(S) if self.ce_weights[s] > 0}
+        drop = train and eng.drop_p > 0
+        eng.forward_core(pl, ws, src_row, key_mask, backward, weighted, drop)
+        # ---- loss (+ dlogits): labels of sequence s live in columns [lab_off, lab_off + len_s + 1)
+        total_n = sum(B * pl.n_out[s] for s in weighted)
+        lab_off = [0]
+        for s in range(S):
+            lab_off.append(lab_off[-1] + ids[s].shape[1] + 1)
+        loss_parts = []
+        for s in sorted(weighted):
+            acc = torch.zeros(2, device=dev)
+            lab_s = labels[:, lab_off[s]:lab_off[s + 1]]
+            q = eng.seqs[s].num_quantizers
+            for gi, (gs, qi, cnt, base) in enumerate(pl.groups):
+                if gs != s:
+                    continue
+                # rows ordered (b, t) <-> label (b, qi + q t): strided view of the label plane, made dense per group
+                lab_g = lab_s[:, qi::q].contiguous().view(-1)
+                scale = self.ce_weights[s] / total_n / self.grad_accum_every
+                lib.cross_entropy(ws["logits"][gi], lab_g, eng.C[s], acc, grad_scale=scale,
+                                  dlogits=ws["dlogits"][gi] if backward else None, rows=B * cnt)
+            loss_parts.append(acc[0] * (self.ce_weights[s] / total_n))
+        loss = torch.stack(loss_parts).sum()
+        self.loss_buf[slot] = loss
+        if backward:
+            eng.backward_core(pl, ws, src_row, key_mask, weighted, drop)
+        return loss
+
+    def _set_hyper(self):
+        t = self.steps + 1
+        fac = 1.0
+        if self.lr_warmup > 0:
+            fac = 1e-7 + (1.0 - 1e-7) * min(self.steps, self.lr_warmup) / self.lr_warmup
+        b1, b2 = self.betas
+        h = self.hyper_host
+        h[0] = self.lr * fac; h[1] = b1; h[2] = b2; h[3] = self.eps; h[4] = self.wd
+        h[5] = 1 - b1 ** t; h[6] = 1 - b2 ** t
+        h[7] = self.max_grad_norm if self.max_grad_norm is not None else 0.0
+        h[8] = 1.0 / self.world
+        self.hyper.copy_(h, non_blocking=True)
+
+    def train_step(self, micro_batches: Sequence[Sequence[torch.Tensor]]):
+        """One optimiser step over `grad_accum_every` micro-batches (each a tuple of token-id tensors in
+        the stage's order, e.g. (clap, semantic, coarse)).  Returns the mean loss as a device scalar."""
+        assert len(micro_batches) == self.grad_accum_every
+        eng = self.eng
+        self.transformer.train()
+        eng.seed += 1
+        for i, mb in enumerate(micro_batches):
+            self._micro_batch(mb, True, i, True)
+        if self.world > 1:
+            dist.all_reduce(eng.arena_g, op=dist.ReduceOp.SUM, group=self.pg)
+        self._set_hyper()
+        eng.sumsq.zero_()
+        if self.max_grad_norm is not None:
+            lib.grad_sumsq(eng.arena_g, eng.sumsq, prescale=1.0 / self.world)
+        lib.adamw_step(eng.arena_p, eng.arena_g, eng.adam_m, eng.adam_v, eng.n_decay, self.hyper, eng.sumsq)
+        eng.arena_g.zero_()
+        eng.refresh_packed(force=True)
+        self.steps += 1
+        return self.loss_buf.sum() / self.grad_accum_every
+
+    @torch.no_grad()
+    def eval_loss(self, token_ids: Sequence[torch.Tensor]):
+        """Wrapper forward in eval mode (no forgetful mask, no dropout): the parity configuration."""
+        self.transformer.eval()
+        return self._micro_batch(token_ids, False, 0, False)
+
+    def grad_norm(self):
+        return torch.sqrt(self.eng.sumsq).float()

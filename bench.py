@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py — coarse-stage training-step throughput of the B200-native hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo (torchrun launches it for N > 1)
+  python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm: the oracle port of the reference path
+
+One "step" = one full optimiser step of the musiclm_small coarse stage (BASELINE.json configs[1]):
+token pre-processing -> embedding gather -> 6 x (attention + conv-FFN) -> logit heads -> CE -> backward ->
+gradient all-reduce (N > 1) -> global-norm clip -> AdamW, training semantics (FFN dropout 0.1 and the 15 %
+forgetful mask active), batch 16 per GPU, N = 1024 positions, synthetic uniform token ids, random-init weights.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(dim=1024, depth=6, heads=8, num_coarse_quantizers=3, attn_dropout=0.0, ff_dropout=0.1, grad_shrink_alpha=0.1)
+SHAPES = dict(clap=12, semantic=197, coarse=(270, 3))          # N = 1 + 13 + 1 + 198 + 1 + 810 = 1024
+TRAIN = dict(lr=3e-4, lr_warmup=6000, wd=0.01, max_grad_norm=0.5, ce_weights=[0.0, 0.0, 1.0])   # configs/training/*.json
+SEQ_N = 1024
+METRIC = "coarse-stage training tokens/sec (positions fed to the transformer per optimiser step / step time)"
+
+
+def synth_batch(B, gen):
+    import torch
+    return [torch.randint(0, 1024, (B, SHAPES["clap"]), generator=gen),
+            torch.randint(0, 1024, (B, SHAPES["semantic"]), generator=gen),
+            torch.randint(0, 1024, (B,) + SHAPES["coarse"], generator=gen)]
+
+
+def flops_per_step(B, N=SEQ_N, L=6, h=8, d=1024):
+    F = int(d * 8 / 3)
+    G = 2 * d * (h * 64) + 2 * d * 128 + 2 * (h * 64) * d + 2 * d * 2 * F + 2 * F * d
+    A = 2 * 64 * h * (N + 1)
+    fwd_attn_ffn = B * N * L * (G + A)
+    conv = B * N * L * 2 * 3 * 2 * F
+    logits = B * 811 * 2 * 1025 * d
+    fwd = fwd_attn_ffn + conv + logits
+    return dict(fwd_attn_ffn=fwd_attn_ffn, fwd=fwd, step=3 * fwd)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], burst=p["bf16_tflops"], sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]), src="measured")
+    return dict(hbm_gbs=6650.0, burst=1590.0, sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], 0, set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx = max(mx, float(c[2]))
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        load = [x for x in sm if x > 0.5 * mx] or sm
+        med = load[len(load) // 2] if load else None
+        return dict(sm_mhz=med, sm_max_mhz=mx or None, reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_arm(steps, warmup, budget_s=150.0):
+    """The reference's own CPU path, as restated by the oracle (kind "port": /root/reference cannot travel to the
+    GPU box): full coarse training step (forward, backward, clip 0.5, AdamW) in fp32 on all host cores, on a
+    bounded sample of the workload (batch 2 instead of 16; CPU throughput is batch-linear)."""
+    import numpy as np
+    import torch
+    from oracle import restatement as R
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = R.coarse_cfg(ce_weights=TRAIN["ce_weights"])
+    params = {k: v for k, v in R.init_state(cfg, seed=0).items()}
+    names = [k for k in params if not k.endswith("beta")]
+    state = {}
+    gen = torch.Generator().manual_seed(1234)
+    Bs = 2
+
+    def one_step(it):
+        toks = [t.numpy() for t in synth_batch(Bs, gen)]
+        sd = {k: (v.clone().requires_grad_(True) if k in names else v) for k, v in params.items()}
+        rng = np.random.default_rng(it)
+        fm = R.forgetful_mask((Bs, SEQ_N), cfg.mask_prob, rng.standard_normal((Bs, SEQ_N)).astype(np.float32))
+        keeps = [torch.from_numpy(rng.random((Bs, SEQ_N, cfg.ff_inner)) >= cfg.ff_dropout) for _ in range(cfg.depth)]
+        loss = R.loss_and_logits(cfg, sd, toks, forget_mask=fm, drop_keeps=keeps)[0]
+        loss.backward()
+        grads = {k: sd[k].grad for k in names}
+        with torch.no_grad():
+            p = {k: params[k] for k in names}
+            R.clip_and_adamw(p, grads, state, step=it, lr=TRAIN["lr"], wd=TRAIN["wd"], max_grad_norm=TRAIN["max_grad_norm"],
+                             warmup_iters=TRAIN["lr_warmup"])
+        return float(loss)
+
+    t_first = time.perf_counter(); one_step(0); t_first = time.perf_counter() - t_first
+    warm_left = max(0, warmup - 1)
+    # keep the whole run within the budget: cap the number of timed steps if a step is slow on this host
+    est = max(t_first * 0.6, 1e-3)
+    steps_eff = max(1, min(steps, int((budget_s - t_first) / est) - warm_left))
+    for i in range(min(warm_left, 2)):
+        one_step(1 + i)
+    times = []
+    for i in range(steps_eff):
+        t0 = time.perf_counter(); one_step(10 + i); times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return dict(tokens_per_s=Bs * SEQ_N / med, ms_per_step=med * 1e3, cores=cores, steps=steps_eff,
+                sample=f"oracle port of the reference training step (fwd+bwd+clip+AdamW, fp32, dropout+forgetful mask on), "
+                       f"batch {Bs} x N {SEQ_N} (1/8 of the GPU batch), median of {steps_eff} steps after warm-up")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_arm(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["tokens_per_s"], "unit": "tokens/s", "n_gpus": args.gpus,
+        "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "musiclm_small coarse-stage training step, N=1024 (BASELINE.json configs[1]), CPU sample batch 2"},
+        "cpu_baseline": {"value": r["tokens_per_s"], "unit": "tokens/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["tokens_per_s"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun for N > 1"
+    import open_musiclm_b200 as O
+    from open_musiclm_b200 import lib
+
+    B = args.batch
+    torch.manual_seed(0)                                      # identical init on every rank (= the reference's init)
+    model = O.create_coarse_transformer(**CFG).cuda()
+    tr = O.HotPathTrainer(model, cross_entropy_loss_weights=TRAIN["ce_weights"], lr=TRAIN["lr"], lr_warmup=TRAIN["lr_warmup"],
+                          wd=TRAIN["wd"], max_grad_norm=TRAIN["max_grad_norm"], grad_accum_every=1, seed=rank)
+    gen = torch.Generator().manual_seed(1234 + rank)
+    pool_host = [[t.pin_memory() for t in synth_batch(B, gen)] for _ in range(8)]
+    pool_dev = [[t.cuda() for t in b] for b in pool_host]
+    h2d = sum(t.numel() * t.element_size() for t in pool_host[0])
+
+    # kernel-launch accounting + GEMM event instrumentation (off during the timed `value` region)
+    launches = {"n": 0}
+    kernels_per_call = {"omlm_attn_bwd": 2, "omlm_ffn_mid_bwd": 2}
+    orig_call = lib.call
+
+    def counting_call(name, *a):
+        launches["n"] += kernels_per_call.get(name, 1)
+        return orig_call(name, *a)
+    lib.call = counting_call
+    gemm_log = []
+    orig_gemm = lib.gemm
+    instrument = {"on": False}
+
+    def timed_gemm(a, b, out, **kw):
+        if not instrument["on"]:
+            return orig_gemm(a, b, out, **kw)
+        a_mn, b_mn = kw.get("a_mn", False), kw.get("b_mn", False)
+        M = kw.get("M") or (a.shape[1] if a_mn else a.shape[0])
+        K = kw.get("K") or (a.shape[0] if a_mn else a.shape[1])
+        Nn = kw.get("N") or (b.shape[1] if b_mn else b.shape[0])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); r = orig_gemm(a, b, out, **kw); e1.record()
+        gemm_log.append((e0, e1, 2.0 * M * Nn * K))
+        return r
+    lib.gemm = timed_gemm
+    import open_musiclm_b200.engine as eng_mod
+    eng_mod.lib.gemm = timed_gemm
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    step_dev = lambda i: tr.train_step([pool_dev[i % len(pool_dev)]])
+    step_e2e = lambda i: float(tr.train_step([pool_host[i % len(pool_host)]]))      # H2D of the batch + D2H of the loss
+
+    for i in range(max(args.warmup, 3)):
+        step_dev(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches["n"] = 0
+    ms_step = timed(step_dev, args.steps)
+    n_launch = launches["n"] // args.steps
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- instrumented steps: GEMM family (the dominant kernel) with one CUDA-event pair per launch
+    instrument["on"] = True
+    ms_instr = timed(step_dev, args.steps)
+    instrument["on"] = False
+    torch.cuda.synchronize()
+    g_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in gemm_log)
+    g_fl = sum(f for _, _, f in gemm_log)
+    n_gemm = len(gemm_log) // args.steps
+    # forward-only (attention + FFN + heads, eval): the north_star's forward roofline figure
+    fwd_fn = lambda i: tr.eval_loss(pool_dev[i % len(pool_dev)])
+    for i in range(3):
+        fwd_fn(i)
+    ms_fwd = timed(fwd_fn, args.steps)
+
+    fl = flops_per_step(B)
+    peaks = load_peaks()
+    tok = world * B * SEQ_N
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_reference_arm(steps=3, warmup=1, budget_s=60.0)
+        cpu = {"value": r["tokens_per_s"], "unit": "tokens/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    if rank == 0:
+        ach = g_fl / (g_ms * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": tok / (ms_step * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "musiclm_small coarse-stage training step (BASELINE.json configs[1]): d=1024 L=6 h=8 conv-FFN F=2730, "
+                                   "N=1024 (clap 12 + semantic 197 + coarse 270x3), dropout 0.1 + forgetful mask 0.15, AdamW + clip 0.5",
+                       "global_batch": world * B, "per_gpu_batch": B, "seq_len": SEQ_N, "parallelism": f"dp{world}",
+                       "l2": "no explicit flush: one step touches > 3 GB of activations/weights, far above the 126 MB L2"},
+            "e2e": {"value": tok / (ms_e2e * 1e-3), "unit": "tokens/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": n_launch * args.steps, "gpu_launches_per_step": n_launch,
+            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all operand-major variants)", "achieved": ach,
+                         "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": ach / peaks["sustained"], "traffic": None,
+                         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']})",
+                         "launches_per_step": n_gemm, "gemm_ms_per_step": g_ms / args.steps,
+                         "gemm_share_of_step": (g_ms / args.steps) / ms_instr, "ms_per_step_instrumented": ms_instr},
+            "step_model_flops": {"tflop_per_step_per_gpu": fl["step"] / 1e12, "achieved_tflops_per_gpu": fl["step"] / (ms_step * 1e-3) / 1e12,
+                                 "frac_of_sustained_peak": fl["step"] / (ms_step * 1e-3) / 1e12 / peaks["sustained"]},
+            "forward_only": {"ms": ms_fwd, "attn_ffn_tflops": fl["fwd_attn_ffn"] / (ms_fwd * 1e-3) / 1e12,
+                             "attn_ffn_frac_of_peak": fl["fwd_attn_ffn"] / (ms_fwd * 1e-3) / 1e12 / peaks["sustained"],
+                             "attn_ffn_frac_of_nominal_2250": fl["fwd_attn_ffn"] / (ms_fwd * 1e-3) / 1e12 / 2250.0},
+            "clocks": clocks,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="per-GPU batch (BASELINE configs[1]: 16)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

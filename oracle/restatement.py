@@ -275,9 +275,11 @@ def logits_from_hidden(cfg: Cfg, sd, hidden, seq_lens: Sequence[int], only_final
             out.append(None)
             continue
         W = sd[f"logit_weights.{s}"]                      # [q, C+1, d]
-        n = hs.shape[1]
-        head = torch.arange(n) % info.num_quantizers                                           # :166-182
-        out.append(torch.einsum("bnd,ncd->bnc", hs, W[head]))
+        n, q = hs.shape[1], info.num_quantizers
+        lg = hs.new_empty(hs.shape[0], n, W.shape[1])
+        for qi in range(min(q, n)):                       # position p uses head p mod q, remainder included (:166-182)
+            lg[:, qi::q] = hs[:, qi::q] @ W[qi].t()
+        out.append(lg)
     return out
 
 

@@ -111,10 +111,11 @@ int omlm_attn_bwd(const void* qn, const void* kvn, const void* d_o, const void* 
 int omlm_ffn_mid_fwd(const void* u, const float* conv_w, const float* gamma, void* hn, float* stats, int B,
                      int N, int F, int Fp, float drop_p, const unsigned long long* seed, int layer,
                      void* stream);
-/* dhn -> du bf16 [B*N, 2Fp]; dgamma [Fp] += ; dconv_w [2Fp,3] += ; dy_scratch bf16 [B*N, 2Fp]. */
-int omlm_ffn_mid_bwd(const void* dhn, const void* u, const float* stats, const float* conv_w, const float* gamma,
-                     void* dy_scratch, void* du, float* dgamma, float* dconv_w, int B, int N, int F, int Fp,
-                     float drop_p, const unsigned long long* seed, int layer, void* stream);
+/* dhn, hn (saved forward output) -> du bf16 [B*N, 2Fp]; dgamma [Fp] += ; dconv_w [2Fp,3] += ;
+ * rowstat_scratch fp32 [B*N, 2]. */
+int omlm_ffn_mid_bwd(const void* dhn, const void* hn, const void* u, const float* stats, const float* conv_w,
+                     const float* gamma, float* rowstat_scratch, void* du, float* dgamma, float* dconv_w, int B, int N,
+                     int F, int Fp, float drop_p, const unsigned long long* seed, int layer, void* stream);
 
 /* ---- cross entropy (open_musiclm.py:401) --------------------------------------------------------
  * loss_acc[0] += sum of row losses, loss_acc[1] += rows counted; dlogits bf16 [rows, ldd] =

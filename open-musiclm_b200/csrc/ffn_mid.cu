@@ -164,146 +164,158 @@ ffn_mid_fwd_kernel(const MidArgs a, __nv_bfloat16* __restrict__ hn, float2* __re
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward, step 1 (row-local): dhn -> (dropout, LN backward) -> dh -> GEGLU backward -> dy [M, 2Fp];
-// dgamma[c] += sum_rows g * hhat.
-__global__ void __launch_bounds__(kMidMaxThreads, 1)
-ffn_mid_bwd_rows_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn,
-                        const float2* __restrict__ stats, __nv_bfloat16* __restrict__ dy,
-                        float* __restrict__ dgamma) {
-  __shared__ float red[kTB * 32];
-  const int slabs = (a.N + kTB - 1) / kTB;
-  const int b = blockIdx.x / slabs, t0 = (blockIdx.x - b * slabs) * kTB;
-  const int chunk = threadIdx.x, c0 = chunk * 8;
-  const bool live = c0 < a.Fp;
+// backward.
+//
+// LayerNorm backward needs two row sums before any element can be finished:
+//   m1 = mean_c(gamma * g),  m2 = mean_c(gamma * g * hhat),   g = dropout-backward(dhn).
+// Since hn = hhat * gamma * mask/(1-p) was saved by the forward pass, gamma*g*hhat == dhn * hn, so both
+// sums come from one cheap pass over (dhn, hn)  [kernel 1, one warp per row].
+// With m1/m2 known the rest is element-local in the channel dimension, so kernel 2 lets every thread own
+// 4 channels (of both GEGLU halves) and WALK DOWN a slab of time steps with sliding windows: it recomputes
+// conv/GEGLU/LN from u, forms dy (never written to memory), applies the transposed causal conv
+// du[t] = w2 dy[t] + w1 dy[t+1] + w0 dy[t+2] and accumulates dconv_w / dgamma in registers.
+__global__ void __launch_bounds__(256)
+ffn_mid_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dhn, const __nv_bfloat16* __restrict__ hn,
+                         const float* __restrict__ gamma, float2* __restrict__ rowstat, long M, int F, int Fp,
+                         float drop_p, const unsigned long long* __restrict__ seed_ptr, uint32_t layer) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * 8 + warp;
+  if (row >= M) return;
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const uint32_t thresh = static_cast<uint32_t>(drop_p * 65536.f);
+  const unsigned long long seed = (drop_p > 0.f) ? *seed_ptr : 0ull;
+  float s1 = 0.f, s2 = 0.f;
+  for (int chunk = lane; chunk * 8 < Fp; chunk += 32) {
+    float d[8], hv[8];
+    load8(dhn + row * Fp + chunk * 8, true, d);
+    load8(hn + row * Fp + chunk * 8, true, hv);
+    bool keep[8];
+    if (drop_p > 0.f) dropout_keep8(seed, layer, row, chunk, thresh, keep);
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + chunk * 8);
+    const float4 g1 = *reinterpret_cast<const float4*>(gamma + chunk * 8 + 4);
+    const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float g = (drop_p > 0.f && !keep[i]) ? 0.f : d[i] * keep_scale;
+      s1 += gm[i] * g;
+      s2 += d[i] * hv[i];
+    }
+  }
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if (lane == 0) rowstat[row] = make_float2(s1 / F, s2 / F);
+}
+
+__device__ __forceinline__ void load4(const __nv_bfloat16* p, bool ok, float (&f)[4]) {
+  uint2 raw = make_uint2(0, 0);
+  if (ok) raw = *reinterpret_cast<const uint2*>(p);
+  const float2 a = unpack_bf16x2(raw.x), b = unpack_bf16x2(raw.y);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+}
+__device__ __forceinline__ void store4(__nv_bfloat16* p, const float (&f)[4]) {
+  uint2 o;
+  o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+  *reinterpret_cast<uint2*>(p) = o;
+}
+
+constexpr int kWalkThreads = 128;
+
+__global__ void __launch_bounds__(kWalkThreads, 4)
+ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, const float2* __restrict__ stats,
+                        const float2* __restrict__ rowstat, __nv_bfloat16* __restrict__ du,
+                        float* __restrict__ dgamma, float* __restrict__ dconv_w, int rows_per_cta) {
+  const int slabs = (a.N + rows_per_cta - 1) / rows_per_cta;
+  const int b = blockIdx.x / slabs, t0 = (blockIdx.x - b * slabs) * rows_per_cta;
+  const int t_end = min(a.N, t0 + rows_per_cta);
+  const int c0 = (blockIdx.y * kWalkThreads + threadIdx.x) * 4;
+  if (c0 >= a.Fp) return;
+  const int chunk8 = c0 >> 3, sub = (c0 >> 2) & 1;  // dropout bits are defined per 8-channel chunk
   const long long row_base = static_cast<long long>(b) * a.N;
   const long ld = 2L * a.Fp;
-  float wa[8][3], wg[8][3], gm[8];
+  float wa[4][3], wg[4][3], gm[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 4; ++i) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      wa[i][k] = live ? a.conv_w[(c0 + i) * 3 + k] : 0.f;
-      wg[i][k] = live ? a.conv_w[(a.Fp + c0 + i) * 3 + k] : 0.f;
-    }
-    gm[i] = live ? a.gamma[c0 + i] : 0.f;
-  }
-  float a2[8], a1[8], g2[8], g1[8];
-  {
-    const bool ok2 = live && t0 - 2 >= 0, ok1 = live && t0 - 1 >= 0;
-    const __nv_bfloat16* p2 = a.u + (row_base + t0 - 2) * ld + c0;
-    const __nv_bfloat16* p1 = a.u + (row_base + t0 - 1) * ld + c0;
-    load8(p2, ok2, a2); load8(p2 + a.Fp, ok2, g2);
-    load8(p1, ok1, a1); load8(p1 + a.Fp, ok1, g1);
+    for (int k = 0; k < 3; ++k) { wa[i][k] = a.conv_w[(c0 + i) * 3 + k]; wg[i][k] = a.conv_w[(a.Fp + c0 + i) * 3 + k]; }
+    gm[i] = a.gamma[c0 + i];
   }
   const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
   const uint32_t thresh = static_cast<uint32_t>(a.drop_p * 65536.f);
   const unsigned long long seed = (a.drop_p > 0.f) ? *a.seed : 0ull;
-  // per row we need ya, yg (recomputed), hhat, gg = gamma * g.  Keep ya/yg as bf16-free floats: 2*8*kTB regs.
-  float ya[kTB][8], yg[kTB][8], gg[kTB][8];
-  float s1[kTB], s2[kTB], dgacc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) dgacc[i] = 0.f;
-#pragma unroll
-  for (int r = 0; r < kTB; ++r) {
-    const bool ok = live && (t0 + r) < a.N;
-    const long long row = row_base + t0 + r;
-    float ac[8], gc[8], gin[8];
-    const __nv_bfloat16* p = a.u + row * ld + c0;
-    load8(p, ok, ac); load8(p + a.Fp, ok, gc);
-    load8(dhn + row * a.Fp + c0, ok, gin);
-    float2 st = make_float2(0.f, 0.f);
-    if ((t0 + r) < a.N) st = stats[row];
-    if (a.drop_p > 0.f && ok) {
-      bool keep[8];
-      dropout_keep8(seed, a.layer, row, chunk, thresh, keep);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) gin[i] = keep[i] ? gin[i] * keep_scale : 0.f;
-    }
-    s1[r] = 0.f; s2[r] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      ya[r][i] = wa[i][0] * a2[i] + wa[i][1] * a1[i] + wa[i][2] * ac[i];
-      yg[r][i] = wg[i][0] * g2[i] + wg[i][1] * g1[i] + wg[i][2] * gc[i];
-      const float hval = gelu_erf(yg[r][i]) * ya[r][i];
-      const float hhat = (c0 + i < a.F) ? (hval - st.x) * st.y : 0.f;
-      dgacc[i] += gin[i] * hhat;
-      gg[r][i] = gin[i] * gm[i];
-      s1[r] += gg[r][i];
-      s2[r] += gg[r][i] * hhat;
-      a2[i] = a1[i]; a1[i] = ac[i]; g2[i] = g1[i]; g1[i] = gc[i];
-    }
+  float ua2[4], ua1[4], ug2[4], ug1[4];           // u rows t'-2, t'-1
+  {
+    const bool ok2 = t0 - 2 >= 0, ok1 = t0 - 1 >= 0;
+    const __nv_bfloat16* p2 = a.u + (row_base + t0 - 2) * ld + c0;
+    const __nv_bfloat16* p1 = a.u + (row_base + t0 - 1) * ld + c0;
+    load4(p2, ok2, ua2); load4(p2 + a.Fp, ok2, ug2);
+    load4(p1, ok1, ua1); load4(p1 + a.Fp, ok1, ug1);
   }
-  block_sum_rows(s1, red);
-  block_sum_rows(s2, red);
+  float da2[4] = {0.f, 0.f, 0.f, 0.f}, da1[4] = {0.f, 0.f, 0.f, 0.f};   // dy rows t'-2, t'-1 (value half)
+  float dg2[4] = {0.f, 0.f, 0.f, 0.f}, dg1[4] = {0.f, 0.f, 0.f, 0.f};   // (gate half)
+  float dwa[4][3], dwg[4][3], dgam[4];
 #pragma unroll
-  for (int r = 0; r < kTB; ++r) {
-    if (t0 + r >= a.N) break;
-    if (!live) continue;
-    const long long row = row_base + t0 + r;
-    const float2 st = stats[row];
-    const float m1 = s1[r] / a.F, m2 = s2[r] / a.F;
-    float da[8], dg[8];
+  for (int i = 0; i < 4; ++i) { dgam[i] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float ge = gelu_erf(yg[r][i]);
-      const float hval = ge * ya[r][i];
-      const float hhat = (hval - st.x) * st.y;
-      const float dh = (c0 + i < a.F) ? st.y * (gg[r][i] - m1 - hhat * m2) : 0.f;
-      da[i] = dh * ge;
-      dg[i] = dh * ya[r][i] * gelu_erf_grad(yg[r][i]);
-    }
-    store8(dy + row * ld + c0, da);
-    store8(dy + row * ld + a.Fp + c0, dg);
-  }
-  if (live) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(&dgamma[c0 + i], dgacc[i]);
-  }
-}
+    for (int k = 0; k < 3; ++k) { dwa[i][k] = 0.f; dwg[i][k] = 0.f; } }
 
-// ------------------------------------------------------------------------------------------------
-// backward, step 2 (conv transpose): du[t,c] = sum_k w[c,k] * dy[t+2-k, c];  dw[c,k] += sum_t dy[t,c] u[t-2+k,c]
-// One CTA = rows_per_cta consecutive time steps of one batch element; thread = 8 channels of [0, 2Fp).
-__global__ void __launch_bounds__(128)
-conv_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ u,
-                const float* __restrict__ conv_w, __nv_bfloat16* __restrict__ du, float* __restrict__ dconv_w,
-                int N, int C /*2Fp*/, int rows_per_cta) {
-  const int slabs = (N + rows_per_cta - 1) / rows_per_cta;
-  const int b = blockIdx.x / slabs, t0 = (blockIdx.x - b * slabs) * rows_per_cta;
-  const int t1 = min(N, t0 + rows_per_cta);
-  const int c0 = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
-  if (c0 >= C) return;
-  const long long row_base = static_cast<long long>(b) * N;
-  float w[8][3], dw[8][3];
+  for (int tp = t0; tp < t_end + 2; ++tp) {
+    const bool valid = tp < a.N;
+    const bool own = tp < t_end;                 // rows >= t_end are the next slab's: recomputed here only for the conv halo
+    const long long row = row_base + tp;
+    float ua0[4], ug0[4], d[4];
+    load4(a.u + row * ld + c0, valid, ua0);
+    load4(a.u + row * ld + a.Fp + c0, valid, ug0);
+    load4(dhn + row * a.Fp + c0, valid, d);
+    float2 st = make_float2(0.f, 0.f), rs = make_float2(0.f, 0.f);
+    if (valid) { st = stats[row]; rs = rowstat[row]; }
+    if (a.drop_p > 0.f && valid) {
+      bool keep[8];
+      dropout_keep8(seed, a.layer, row, chunk8, thresh, keep);
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { w[i][k] = conv_w[(c0 + i) * 3 + k]; dw[i][k] = 0.f; }
-  // sliding windows: dy rows t, t+1, t+2 ; u rows t-2, t-1, t
-  float d0[8], d1[8], d2[8], u2[8], u1[8], u0[8];
-  load8(dy + (row_base + t0) * C + c0, t0 < N, d0);
-  load8(dy + (row_base + t0 + 1) * C + c0, t0 + 1 < N, d1);
-  load8(u + (row_base + t0 - 2) * C + c0, t0 - 2 >= 0, u2);
-  load8(u + (row_base + t0 - 1) * C + c0, t0 - 1 >= 0, u1);
-  for (int t = t0; t < t1; ++t) {
-    load8(dy + (row_base + t + 2) * C + c0, t + 2 < N, d2);
-    load8(u + (row_base + t) * C + c0, true, u0);
-    float o[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      // y[t] = w0 u[t-2] + w1 u[t-1] + w2 u[t]  =>  du[t] = w2 dy[t] + w1 dy[t+1] + w0 dy[t+2]
-      o[i] = w[i][2] * d0[i] + w[i][1] * d1[i] + w[i][0] * d2[i];
-      dw[i][0] += d0[i] * u2[i];
-      dw[i][1] += d0[i] * u1[i];
-      dw[i][2] += d0[i] * u0[i];
-      d0[i] = d1[i]; d1[i] = d2[i]; u2[i] = u1[i]; u1[i] = u0[i];
+      for (int i = 0; i < 4; ++i) d[i] = keep[sub * 4 + i] ? d[i] * keep_scale : 0.f;
     }
-    store8(du + (row_base + t) * C + c0, o);
+    float da0[4], dg0[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float ya = wa[i][0] * ua2[i] + wa[i][1] * ua1[i] + wa[i][2] * ua0[i];
+      const float yg = wg[i][0] * ug2[i] + wg[i][1] * ug1[i] + wg[i][2] * ug0[i];
+      const float phi = 0.5f * (1.f + erff(yg * 0.70710678118654752f));
+      const float ge = yg * phi;
+      const float hhat = (ge * ya - st.x) * st.y;
+      const bool real = valid && (c0 + i < a.F);
+      const float dh = real ? st.y * (gm[i] * d[i] - rs.x - hhat * rs.y) : 0.f;
+      da0[i] = dh * ge;
+      dg0[i] = dh * ya * (phi + yg * 0.3989422804014327f * __expf(-0.5f * yg * yg));
+      if (own && real) {
+        dgam[i] += d[i] * hhat;
+        dwa[i][0] += da0[i] * ua2[i]; dwa[i][1] += da0[i] * ua1[i]; dwa[i][2] += da0[i] * ua0[i];
+        dwg[i][0] += dg0[i] * ug2[i]; dwg[i][1] += dg0[i] * ug1[i]; dwg[i][2] += dg0[i] * ug0[i];
+      }
+    }
+    if (tp - 2 >= t0) {  // du[t'-2] = w2 dy[t'-2] + w1 dy[t'-1] + w0 dy[t']
+      float oa[4], og[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        oa[i] = wa[i][2] * da2[i] + wa[i][1] * da1[i] + wa[i][0] * da0[i];
+        og[i] = wg[i][2] * dg2[i] + wg[i][1] * dg1[i] + wg[i][0] * dg0[i];
+      }
+      store4(du + (row - 2) * ld + c0, oa);
+      store4(du + (row - 2) * ld + a.Fp + c0, og);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ua2[i] = ua1[i]; ua1[i] = ua0[i]; ug2[i] = ug1[i]; ug1[i] = ug0[i];
+      da2[i] = da1[i]; da1[i] = da0[i]; dg2[i] = dg1[i]; dg1[i] = dg0[i];
+    }
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 4; ++i) {
+    atomicAdd(&dgamma[c0 + i], dgam[i]);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) atomicAdd(&dconv_w[(c0 + i) * 3 + k], dw[i][k]);
+    for (int k = 0; k < 3; ++k) {
+      atomicAdd(&dconv_w[(c0 + i) * 3 + k], dwa[i][k]);
+      atomicAdd(&dconv_w[(a.Fp + c0 + i) * 3 + k], dwg[i][k]);
+    }
+  }
 }
 
 static int mid_threads(int Fp) { return ((Fp / 8 + 31) / 32) * 32; }
@@ -326,25 +338,24 @@ int omlm_ffn_mid_fwd(const void* u, const float* conv_w, const float* gamma, voi
   return 0;
 }
 
-int omlm_ffn_mid_bwd(const void* dhn, const void* u, const float* stats, const float* conv_w, const float* gamma,
-                     void* dy_scratch, void* du, float* dgamma, float* dconv_w, int B, int N, int F, int Fp,
-                     float drop_p, const unsigned long long* seed, int layer, void* stream) {
+int omlm_ffn_mid_bwd(const void* dhn, const void* hn, const void* u, const float* stats, const float* conv_w,
+                     const float* gamma, float* rowstat_scratch, void* du, float* dgamma, float* dconv_w, int B, int N,
+                     int F, int Fp, float drop_p, const unsigned long long* seed, int layer, void* stream) {
   using namespace omlm;
   OMLM_CHECK_ARG(B > 0 && N > 0 && F > 0 && Fp >= F && Fp % 8 == 0 && Fp <= 8 * kMidMaxThreads, "ffn_mid_bwd: bad shape F=%d Fp=%d", F, Fp);
   auto st = reinterpret_cast<cudaStream_t>(stream);
   MidArgs a{reinterpret_cast<const __nv_bfloat16*>(u), conv_w, gamma, N, F, Fp, drop_p, seed, static_cast<uint32_t>(layer)};
-  const int slabs = (N + kTB - 1) / kTB;
-  ffn_mid_bwd_rows_kernel<<<B * slabs, mid_threads(Fp), 0, st>>>(
-      a, reinterpret_cast<const __nv_bfloat16*>(dhn), reinterpret_cast<const float2*>(stats),
-      reinterpret_cast<__nv_bfloat16*>(dy_scratch), dgamma);
+  const long M = static_cast<long>(B) * N;
+  ffn_mid_bwd_stats_kernel<<<static_cast<int>((M + 7) / 8), 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dhn), reinterpret_cast<const __nv_bfloat16*>(hn), gamma,
+      reinterpret_cast<float2*>(rowstat_scratch), M, F, Fp, drop_p, seed, static_cast<uint32_t>(layer));
   OMLM_LAUNCH_CHECK();
-  const int C = 2 * Fp;
   const int rows_per_cta = 32;
-  const int threads = 128;
-  dim3 grid(B * ((N + rows_per_cta - 1) / rows_per_cta), (C / 8 + threads - 1) / threads);
-  conv_bwd_kernel<<<grid, threads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy_scratch),
-                                            reinterpret_cast<const __nv_bfloat16*>(u), conv_w,
-                                            reinterpret_cast<__nv_bfloat16*>(du), dconv_w, N, C, rows_per_cta);
+  dim3 grid(B * ((N + rows_per_cta - 1) / rows_per_cta), (Fp / 4 + kWalkThreads - 1) / kWalkThreads);
+  ffn_mid_bwd_walk_kernel<<<grid, kWalkThreads, 0, st>>>(a, reinterpret_cast<const __nv_bfloat16*>(dhn),
+                                                         reinterpret_cast<const float2*>(stats),
+                                                         reinterpret_cast<const float2*>(rowstat_scratch),
+                                                         reinterpret_cast<__nv_bfloat16*>(du), dgamma, dconv_w, rows_per_cta);
   OMLM_LAUNCH_CHECK();
   return 0;
 }

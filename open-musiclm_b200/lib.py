@@ -191,8 +191,8 @@ def ffn_mid_fwd(u, conv_w, gamma, hn, stats, B, N, F, Fp, drop_p=0.0, seed=None,
          _F(drop_p), _p(seed), _I(layer), _stream())
 
 
-def ffn_mid_bwd(dhn, u, stats, conv_w, gamma, dy_scratch, du, dgamma, dconv_w, B, N, F, Fp, drop_p=0.0, seed=None, layer=0):
-    call("omlm_ffn_mid_bwd", _p(dhn), _p(u), _p(stats), _p(conv_w), _p(gamma), _p(dy_scratch), _p(du), _p(dgamma),
+def ffn_mid_bwd(dhn, hn, u, stats, conv_w, gamma, rowstat, du, dgamma, dconv_w, B, N, F, Fp, drop_p=0.0, seed=None, layer=0):
+    call("omlm_ffn_mid_bwd", _p(dhn), _p(hn), _p(u), _p(stats), _p(conv_w), _p(gamma), _p(rowstat), _p(du), _p(dgamma),
          _p(dconv_w), _I(B), _I(N), _I(F), _I(Fp), _F(drop_p), _p(seed), _I(layer), _stream())
 
 

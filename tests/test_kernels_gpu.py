@@ -253,9 +253,9 @@ def test_ffn_mid_fwd_bwd(lib, B, N, F_, Fp, drop_p):
     dhn = torch.zeros(M, Fp, device=DEV, dtype=torch.bfloat16)
     dhn[:, :F_] = torch.randn(M, F_, device=DEV).bfloat16()
     ref.backward(dhn[:, :F_].float())
-    dy = torch.empty(M, 2 * Fp, device=DEV, dtype=torch.bfloat16); du = torch.empty_like(dy)
+    du = torch.empty(M, 2 * Fp, device=DEV, dtype=torch.bfloat16); rowstat = torch.empty(M, 2, device=DEV)
     dg = torch.zeros(Fp, device=DEV); dcw = torch.zeros(2 * Fp, 3, device=DEV)
-    lib.ffn_mid_bwd(dhn, u, stats, cwp, gp, dy, du, dg, dcw, B, N, F_, Fp, drop_p, seed, 3)
+    lib.ffn_mid_bwd(dhn, hn, u, stats, cwp, gp, rowstat, du, dg, dcw, B, N, F_, Fp, drop_p, seed, 3)
     du_real = torch.cat([du[:, :F_], du[:, Fp:Fp + F_]], 1)
     assert rel(du_real, uf.grad) < 1.2e-2
     assert rel(dg[:F_], gr.grad) < 5e-3

@@ -89,7 +89,11 @@ int omlm_qk_l2norm_bwd(const float* dqn, const float* dkvn, const void* q_raw, c
 int omlm_sgemm_small(const float* A, long sa_m, long sa_k, const float* B, long sb_k, long sb_n, float* C,
                      long sc_m, long sc_n, float* Z, const float* bias, int M, int N, int K, int act,
                      int accumulate, void* stream);
-int omlm_silu_bwd(const float* dA, const float* Z, float* dZ, long n, void* stream);
+int omlm_silu_bwd(const float* dA, const float* Z, float* dZ, void* dZ_bf16, long n, void* stream);
+/* bf16x3 operand split for near-fp32 products on the tensor cores: dst bf16 [R, 3C] = [hi|hi|lo] (activations)
+ * or [hi|lo|hi] (weight_mode);  bias_silu: z += bias, a = silu(z). */
+int omlm_split3_bf16(const float* src, long src_ld, void* dst, int R, int C, int weight_mode, void* stream);
+int omlm_bias_silu(float* z, const float* bias, float* a, int R, int C, void* stream);
 int omlm_colsum(const float* X, long s_m, long s_n, float* out, int M, int N, int accumulate, void* stream);
 int omlm_arange_f32(float* out, int n, void* stream);
 

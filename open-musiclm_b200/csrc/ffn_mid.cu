@@ -16,9 +16,25 @@ constexpr int kT = 8;   // time steps per slab (forward)
 constexpr int kTB = 4;  // time steps per slab (backward: three live values per element)
 constexpr int kMidMaxThreads = 384;
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+// Exact-erf GELU pieces from ONE exponential: e = exp(-x^2/2) gives both the normal pdf and, through the
+// Abramowitz-Stegun 7.1.26 rational form (|error| <= 1.5e-7, below fp32 resolution of the products here),
+// erf(x/sqrt(2)).  cdf = Phi(x), pdf = phi(x);  gelu(x) = x*cdf, gelu'(x) = cdf + x*pdf.
+__device__ __forceinline__ void normal_cdf_pdf(float x, float& cdf, float& pdf) {
+  const float e = __expf(-0.5f * x * x);
+  const float ax = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float half_erfc = 0.5f * p * t * e;            // 0.5 * erfc(|x|/sqrt2)
+  cdf = x >= 0.f ? 1.f - half_erfc : half_erfc;
+  pdf = 0.3989422804014327f * e;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float c, p;
+  normal_cdf_pdf(x, c, p);
+  return x * c;
 }
 
 __device__ __forceinline__ void load8(const __nv_bfloat16* p, bool ok, float (&f)[8]) {
@@ -278,13 +294,14 @@ ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, 
     for (int i = 0; i < 4; ++i) {
       const float ya = wa[i][0] * ua2[i] + wa[i][1] * ua1[i] + wa[i][2] * ua0[i];
       const float yg = wg[i][0] * ug2[i] + wg[i][1] * ug1[i] + wg[i][2] * ug0[i];
-      const float phi = 0.5f * (1.f + erff(yg * 0.70710678118654752f));
+      float phi, pdf;
+      normal_cdf_pdf(yg, phi, pdf);
       const float ge = yg * phi;
       const float hhat = (ge * ya - st.x) * st.y;
       const bool real = valid && (c0 + i < a.F);
       const float dh = real ? st.y * (gm[i] * d[i] - rs.x - hhat * rs.y) : 0.f;
       da0[i] = dh * ge;
-      dg0[i] = dh * ya * (phi + yg * 0.3989422804014327f * __expf(-0.5f * yg * yg));
+      dg0[i] = dh * ya * fmaf(yg, pdf, phi);
       if (own && real) {
         dgam[i] += d[i] * hhat;
         dwa[i][0] += da0[i] * ua2[i]; dwa[i][1] += da0[i] * ua1[i]; dwa[i][2] += da0[i] * ua0[i];

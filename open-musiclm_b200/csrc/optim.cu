@@ -65,15 +65,41 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
 template <typename OutT>
 __global__ void pack_kernel(const float* __restrict__ src, long src_ld, int rows_valid, int cols_valid,
                             OutT* __restrict__ dst, long dst_ld, int rows_p, int cols_p, int split_dst, int split_src) {
-  const long total = static_cast<long>(rows_p) * cols_p;
+  // one thread per 4 consecutive columns of a destination row
+  const int c4n = (cols_p + 3) >> 2;
+  const long total = static_cast<long>(rows_p) * c4n;
+  const bool vec_src = ((src_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  const bool vec_dst = ((dst_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((cols_p & 3) == 0);
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(i / cols_p), c = static_cast<int>(i - static_cast<long>(r) * cols_p);
+    const int r = static_cast<int>(i / c4n), c = static_cast<int>(i - static_cast<long>(r) * c4n) << 2;
     int sr = r; bool live = r < rows_valid;
-    if (split_dst > 0) { const int half = r / split_dst, rr = r - half * split_dst; live = rr < split_src; sr = half * split_src + rr; live = live && sr < rows_valid; }
-    float val = 0.f;
-    if (live && c < cols_valid) val = src[sr * src_ld + c];
-    if constexpr (sizeof(OutT) == 2) dst[r * dst_ld + c] = __float2bfloat16_rn(val);
-    else dst[r * dst_ld + c] = val;
+    if (split_dst > 0) { const int half = r / split_dst, rr = r - half * split_dst; sr = half * split_src + rr; live = rr < split_src && sr < rows_valid; }
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (live) {
+      if (vec_src && c + 3 < cols_valid) {
+        const float4 t = *reinterpret_cast<const float4*>(src + sr * src_ld + c);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (c + j < cols_valid) v[j] = src[sr * src_ld + c + j];
+      }
+    }
+    OutT* d = dst + r * dst_ld + c;
+    if (vec_dst) {
+      if constexpr (sizeof(OutT) == 2) {
+        uint2 o; o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+        *reinterpret_cast<uint2*>(d) = o;
+      } else {
+        *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (c + j < cols_p) {
+          if constexpr (sizeof(OutT) == 2) d[j] = __float2bfloat16_rn(v[j]); else d[j] = v[j];
+        }
+      }
+    }
   }
 }
 
@@ -118,8 +144,8 @@ int omlm_pack(const float* src, long src_ld, int rows_valid, int cols_valid, voi
               int rows_p, int cols_p, int split_dst, int split_src, void* stream) {
   using namespace omlm;
   OMLM_CHECK_ARG(rows_p > 0 && cols_p > 0, "pack: empty");
-  const long total = static_cast<long>(rows_p) * cols_p;
-  const int blocks = static_cast<int>(std::min<long>((total + 255) / 256, static_cast<long>(num_sms()) * 8));
+  const long total = static_cast<long>(rows_p) * ((cols_p + 3) / 4);
+  const int blocks = static_cast<int>(std::min<long>((total + 255) / 256, static_cast<long>(num_sms()) * 16));
   auto st = reinterpret_cast<cudaStream_t>(stream);
   if (dst_f32)
     pack_kernel<float><<<blocks, 256, 0, st>>>(src, src_ld, rows_valid, cols_valid, reinterpret_cast<float*>(dst), dst_ld, rows_p, cols_p, split_dst, split_src);

@@ -66,12 +66,14 @@ sgemm_small_kernel(const float* __restrict__ A, long sa_m, long sa_k, const floa
 
 // dZ = dA * silu'(z),  silu'(z) = s + z*s*(1-s), s = sigmoid(z)
 __global__ void silu_bwd_kernel(const float* __restrict__ dA, const float* __restrict__ Zp,
-                                float* __restrict__ dZ, long n) {
+                                float* __restrict__ dZ, __nv_bfloat16* __restrict__ dZ_bf16, long n) {
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
     const float z = Zp[i];
     const float s = 1.f / (1.f + expf(-z));
-    dZ[i] = dA[i] * (s + z * s * (1.f - s));
+    const float g = dA[i] * (s + z * s * (1.f - s));
+    dZ[i] = g;
+    if (dZ_bf16 != nullptr) dZ_bf16[i] = __float2bfloat16_rn(g);
   }
 }
 
@@ -89,6 +91,35 @@ __global__ void colsum_kernel(const float* __restrict__ X, long s_m, long s_n, f
     float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
     v = warp_sum(v);
     if (threadIdx.x == 0) out[n] = accumulate ? out[n] + v : v;
+  }
+}
+
+// bf16x3 split for near-fp32 tensor-core products:  x = hi + lo (both bf16).  With
+//   A3 = [a_hi | a_hi | a_lo]  and  W3 = [w_hi | w_lo | w_hi]   (K concatenated),
+// A3 . W3^T = a_hi w_hi + a_hi w_lo + a_lo w_hi  ~  a . w  to ~2^-16 relative, accumulated in fp32 by tcgen05.
+__global__ void split3_kernel(const float* __restrict__ src, long src_ld, __nv_bfloat16* __restrict__ dst, int R,
+                              int C, int weight_mode) {
+  const long total = static_cast<long>(R) * C;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / C), c = static_cast<int>(i - static_cast<long>(r) * C);
+    const float v = src[r * src_ld + c];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    __nv_bfloat16* d = dst + static_cast<long>(r) * 3 * C + c;
+    d[0] = hi;
+    d[C] = weight_mode ? lo : hi;
+    d[2 * C] = weight_mode ? hi : lo;
+  }
+}
+
+// z += bias (in place);  a = silu(z)
+__global__ void bias_silu_kernel(float* __restrict__ z, const float* __restrict__ bias, float* __restrict__ a, int R, int C) {
+  const long total = static_cast<long>(R) * C;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const float v = z[i] + bias[c];
+    z[i] = v;
+    a[i] = v / (1.f + expf(-v));
   }
 }
 
@@ -113,11 +144,11 @@ int omlm_sgemm_small(const float* A, long sa_m, long sa_k, const float* B, long 
   return 0;
 }
 
-int omlm_silu_bwd(const float* dA, const float* Z, float* dZ, long n, void* stream) {
+int omlm_silu_bwd(const float* dA, const float* Z, float* dZ, void* dZ_bf16, long n, void* stream) {
   using namespace omlm;
   OMLM_CHECK_ARG(n > 0, "silu_bwd: empty");
   const int blocks = static_cast<int>(std::min<long>((n + 255) / 256, 4096));
-  silu_bwd_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dA, Z, dZ, n);
+  silu_bwd_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dA, Z, dZ, reinterpret_cast<__nv_bfloat16*>(dZ_bf16), n);
   OMLM_LAUNCH_CHECK();
   return 0;
 }
@@ -126,6 +157,26 @@ int omlm_colsum(const float* X, long s_m, long s_n, float* out, int M, int N, in
   using namespace omlm;
   OMLM_CHECK_ARG(M > 0 && N > 0, "colsum: empty");
   colsum_kernel<<<N, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(X, s_m, s_n, out, M, N, accumulate);
+  OMLM_LAUNCH_CHECK();
+  return 0;
+}
+
+int omlm_split3_bf16(const float* src, long src_ld, void* dst, int R, int C, int weight_mode, void* stream) {
+  using namespace omlm;
+  OMLM_CHECK_ARG(R > 0 && C > 0, "split3: empty");
+  const long total = static_cast<long>(R) * C;
+  const int blocks = static_cast<int>(std::min<long>((total + 255) / 256, 2048));
+  split3_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, src_ld, reinterpret_cast<__nv_bfloat16*>(dst), R, C, weight_mode);
+  OMLM_LAUNCH_CHECK();
+  return 0;
+}
+
+int omlm_bias_silu(float* z, const float* bias, float* a, int R, int C, void* stream) {
+  using namespace omlm;
+  OMLM_CHECK_ARG(R > 0 && C > 0, "bias_silu: empty");
+  const long total = static_cast<long>(R) * C;
+  const int blocks = static_cast<int>(std::min<long>((total + 255) / 256, 2048));
+  bias_silu_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(z, bias, a, R, C);
   OMLM_LAUNCH_CHECK();
   return 0;
 }

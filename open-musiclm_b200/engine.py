@@ -159,6 +159,7 @@ class Engine:
                 w2=torch.empty(d, Fp, device=dev, dtype=bf), conv=torch.empty(2 * Fp, 3, device=dev),
                 gin=torch.empty(Fp, device=dev)))
         self.pk_logit = [torch.empty(s.num_quantizers, cp, d, device=dev, dtype=bf) for s, cp in zip(self.seqs, self.Cp)]
+        self.pk_rp = [torch.empty(self.Hr, 3 * self.Hr, device=dev, dtype=bf) for _ in range(2)]   # rel-pos MLP layers 1, 2: [hi|lo|hi]
 
     def refresh_packed(self, force=False):
         ver = self.params_version()
@@ -179,6 +180,8 @@ class Engine:
             # [q, C, d] -> [q, Cp, d]: every head padded with zero rows
             lib.pack(pv[f"logit_weights.{s}"], d, seq.num_quantizers * self.C[s], d, self.pk_logit[s].view(-1, d),
                      seq.num_quantizers * self.Cp[s], d, split_dst=self.Cp[s], split_src=self.C[s])
+        for j in (1, 2):
+            lib.split3_bf16(pv[f"transformer.rel_pos_bias.net.{j}.0.weight"], self.pk_rp[j - 1], weight_mode=True)
         self._packed_version = ver
 
     # ------------------------------------------------------------------------------------------ plans / workspaces
@@ -209,6 +212,7 @@ class Engine:
             # rel-pos MLP
             rp_in=E(pl.N, 1, dt=f32), rp_z=[E(pl.N, self.Hr, dt=f32) for _ in range(3)],
             rp_a=[E(pl.N, self.Hr, dt=f32) for _ in range(3)], table=E(h, pl.N, dt=f32),
+            rp_a3=[E(pl.N, 3 * self.Hr) for _ in range(2)],
         )
         lib.arange_f32(ws["rp_in"])
         if train:
@@ -219,7 +223,7 @@ class Engine:
                 d_o=E(M, HD), dqn=E(M, HD, dt=f32), dkvn=E(M, 128, dt=f32), dsum=E(M * h, dt=f32),
                 dq_raw=E(M, HD), dkv_raw=E(M, 128), dtable=E(h, pl.N, dt=f32),
                 dgin=E(Fp, dt=f32), dconv=E(2 * Fp, 3, dt=f32),
-                rp_d0=E(pl.N, self.Hr, dt=f32), rp_d1=E(pl.N, self.Hr, dt=f32),
+                rp_d0=E(pl.N, self.Hr, dt=f32), rp_d1=E(pl.N, self.Hr, dt=f32), rp_dz_bf=E(pl.N, self.Hr),
             )
         self._ws[key] = ws
         return ws
@@ -247,16 +251,18 @@ class Engine:
         return 256 if N % 256 == 0 or N >= 2048 else 128
 
     def _relpos_table(self, ws, N):
-        """RelativePositionBias MLP on the causal distances 0..N-1 -> table[h, N] (transformer.py:55-67)."""
+        """RelativePositionBias MLP on the causal distances 0..N-1 -> table[h, N] (transformer.py:55-67).
+        The two Hr x Hr layers run on the tcgen05 GEMM with bf16x3-split operands (fp32-class accuracy: the
+        table reaches |b| ~ 100 and dominates the logits); the rank-1 first layer and the h-wide last layer are SIMT."""
         pv, Hr, h = self.pview, self.Hr, self.h
         pre = "transformer.rel_pos_bias.net."
-        a = ws["rp_in"]
-        K = 1
-        for j in range(3):
-            W, b = pv[f"{pre}{j}.0.weight"], pv[f"{pre}{j}.0.bias"]
-            lib.sgemm_small(a, (K, 1), W, (1, K), ws["rp_a"][j], (Hr, 1), N, Hr, K, Z=ws["rp_z"][j], bias=b, act=1)
-            a, K = ws["rp_a"][j], Hr
-        lib.sgemm_small(a, (Hr, 1), pv[pre + "3.weight"], (1, Hr), ws["table"], (1, N), N, h, Hr, bias=pv[pre + "3.bias"])
+        lib.sgemm_small(ws["rp_in"], (1, 1), pv[pre + "0.0.weight"], (1, 1), ws["rp_a"][0], (Hr, 1), N, Hr, 1,
+                        Z=ws["rp_z"][0], bias=pv[pre + "0.0.bias"], act=1)
+        for j in (1, 2):
+            lib.split3_bf16(ws["rp_a"][j - 1], ws["rp_a3"][j - 1])
+            lib.gemm(ws["rp_a3"][j - 1], self.pk_rp[j - 1], ws["rp_z"][j], block_n=128)
+            lib.bias_silu(ws["rp_z"][j], pv[f"{pre}{j}.0.bias"], ws["rp_a"][j])
+        lib.sgemm_small(ws["rp_a"][2], (Hr, 1), pv[pre + "3.weight"], (1, Hr), ws["table"], (1, N), N, h, Hr, bias=pv[pre + "3.bias"])
 
     def forward_core(self, pl: _Plan, ws, src_row, key_mask, train: bool, groups_wanted=None, drop: bool = False):
         """Runs embeddings -> depth x (attention, conv-FFN) -> final LN -> logit heads.  Activations stay in `ws`."""
@@ -367,13 +373,16 @@ class Engine:
         d_cur, d_nxt = ws["rp_d0"], ws["rp_d1"]
         lib.sgemm_small(dT, (1, N), pv[pre + "3.weight"], (Hr, 1), d_cur, (Hr, 1), N, Hr, h)                      # da3 = dY W4
         for j in (2, 1, 0):
-            lib.silu_bwd(d_cur, ws["rp_z"][j], d_cur)                                                             # dz_j
-            a_prev, K = (ws["rp_a"][j - 1], Hr) if j > 0 else (ws["rp_in"], 1)
-            lib.sgemm_small(d_cur, (1, Hr), a_prev, (K, 1), gv[f"{pre}{j}.0.weight"], (K, 1), Hr, K, N, accumulate=True)
+            lib.silu_bwd(d_cur, ws["rp_z"][j], d_cur, ws["rp_dz_bf"] if j > 0 else None)                           # dz_j
             lib.colsum(d_cur, Hr, 1, gv[f"{pre}{j}.0.bias"], N, Hr, accumulate=True)
             if j > 0:
-                lib.sgemm_small(d_cur, (Hr, 1), pv[f"{pre}{j}.0.weight"], (Hr, 1), d_nxt, (Hr, 1), N, Hr, Hr)     # da_{j-1} = dz_j W_j
+                a_hi = ws["rp_a3"][j - 1][:, :Hr]          # bf16 hi part of a_{j-1}, saved by the forward split
+                gw = gv[f"{pre}{j}.0.weight"]
+                lib.gemm(ws["rp_dz_bf"], a_hi, gw, a_mn=True, b_mn=True, M=Hr, N=Hr, K=N, addend=gw, block_n=128)  # dW_j += dz^T a
+                lib.gemm(ws["rp_dz_bf"], self.pk_rp[j - 1][:, :Hr], d_nxt, b_mn=True, M=N, N=Hr, K=Hr, block_n=128)  # da = dz W_hi
                 d_cur, d_nxt = d_nxt, d_cur
+            else:
+                lib.sgemm_small(d_cur, (1, Hr), ws["rp_in"], (1, 1), gv[f"{pre}0.0.weight"], (1, 1), Hr, 1, N, accumulate=True)
 
     # ------------------------------------------------------------------------------------------ reference-API path
     def api_forward(self, all_token_ids, self_attn_mask, only_final):

@@ -164,8 +164,18 @@ def sgemm_small(A, sa, B, sb, C, sc, M, N, K, *, Z=None, bias=None, act=0, accum
          _p(Z), _p(bias), _I(M), _I(N), _I(K), _I(act), _I(int(accumulate)), _stream())
 
 
-def silu_bwd(dA, Z, dZ):
-    call("omlm_silu_bwd", _p(dA), _p(Z), _p(dZ), _L(dA.numel()), _stream())
+def silu_bwd(dA, Z, dZ, dZ_bf16=None):
+    call("omlm_silu_bwd", _p(dA), _p(Z), _p(dZ), _p(dZ_bf16), _L(dA.numel()), _stream())
+
+
+def split3_bf16(src, dst, weight_mode=False):
+    R, C = src.shape
+    call("omlm_split3_bf16", _p(src), _L(src.stride(0)), _p(dst), _I(R), _I(C), _I(int(weight_mode)), _stream())
+
+
+def bias_silu(z, bias, a):
+    R, C = z.shape
+    call("omlm_bias_silu", _p(z), _p(bias), _p(a), _I(R), _I(C), _stream())
 
 
 def colsum(X, s_m, s_n, out, M, N, accumulate=False):

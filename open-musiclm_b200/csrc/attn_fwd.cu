@@ -26,7 +26,7 @@ struct AttnFwdSmem {
   float kneg[2][kAttnBC];
 };
 
-__global__ void __launch_bounds__(kAttnThreads, 1)
+__global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qn, const __nv_bfloat16* __restrict__ kvn,
                 const float* __restrict__ table, int table_ld, const unsigned char* __restrict__ key_mask,
                 __nv_bfloat16* __restrict__ out, float* __restrict__ lse2, int N, int h, float scale) {

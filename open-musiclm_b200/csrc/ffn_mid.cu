@@ -94,43 +94,60 @@ struct MidArgs {
 };
 
 // ------------------------------------------------------------------------------------------------
-// forward: hn = dropout(LN(gelu(conv(u)_gate) * conv(u)_value)),  stats = (mean, rstd) per row
-__global__ void __launch_bounds__(kMidMaxThreads, 1)
+// forward: hn = dropout(LN(gelu(conv(u)_gate) * conv(u)_value)),  stats = (mean, rstd) per row.
+// 4 channels per thread (of both halves): Fp/4 threads = 22 warps per CTA at Fp = 2752, one CTA per SM.
+constexpr int kFwdCh = 4;
+constexpr int kFwdMaxThreads = 704;
+
+__device__ __forceinline__ void load4(const __nv_bfloat16* p, bool ok, float (&f)[4]) {
+  uint2 raw = make_uint2(0, 0);
+  if (ok) raw = *reinterpret_cast<const uint2*>(p);
+  const float2 a = unpack_bf16x2(raw.x), b = unpack_bf16x2(raw.y);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+}
+__device__ __forceinline__ void store4(__nv_bfloat16* p, const float (&f)[4]) {
+  uint2 o;
+  o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+  *reinterpret_cast<uint2*>(p) = o;
+}
+
+__global__ void __launch_bounds__(kFwdMaxThreads, 1)
 ffn_mid_fwd_kernel(const MidArgs a, __nv_bfloat16* __restrict__ hn, float2* __restrict__ stats) {
   __shared__ float red[kT * 32];
   const int slabs = (a.N + kT - 1) / kT;
   const int b = blockIdx.x / slabs, t0 = (blockIdx.x - b * slabs) * kT;
-  const int chunk = threadIdx.x, c0 = chunk * 8;
+  const int c0 = threadIdx.x * kFwdCh;
+  const int chunk8 = c0 >> 3, sub = threadIdx.x & 1;
   const bool live = c0 < a.Fp;
   const long long row_base = static_cast<long long>(b) * a.N;
   const long ld = 2L * a.Fp;
-  float wa[8][3], wg[8][3];
+  float wa[kFwdCh][3], wg[kFwdCh][3];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < kFwdCh; ++i)
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       wa[i][k] = live ? a.conv_w[(c0 + i) * 3 + k] : 0.f;
       wg[i][k] = live ? a.conv_w[(a.Fp + c0 + i) * 3 + k] : 0.f;
     }
-  float a2[8], a1[8], g2[8], g1[8];
+  float a2[kFwdCh], a1[kFwdCh], g2[kFwdCh], g1[kFwdCh];
   {
     const bool ok2 = live && t0 - 2 >= 0, ok1 = live && t0 - 1 >= 0;
     const __nv_bfloat16* p2 = a.u + (row_base + t0 - 2) * ld + c0;
     const __nv_bfloat16* p1 = a.u + (row_base + t0 - 1) * ld + c0;
-    load8(p2, ok2, a2); load8(p2 + a.Fp, ok2, g2);
-    load8(p1, ok1, a1); load8(p1 + a.Fp, ok1, g1);
+    load4(p2, ok2, a2); load4(p2 + a.Fp, ok2, g2);
+    load4(p1, ok1, a1); load4(p1 + a.Fp, ok1, g1);
   }
-  float hv[kT][8];
+  float hv[kT][kFwdCh];
   float s[kT];
 #pragma unroll
   for (int r = 0; r < kT; ++r) {
     const bool ok = live && (t0 + r) < a.N;
-    float ac[8], gc[8];
+    float ac[kFwdCh], gc[kFwdCh];
     const __nv_bfloat16* p = a.u + (row_base + t0 + r) * ld + c0;
-    load8(p, ok, ac); load8(p + a.Fp, ok, gc);
+    load4(p, ok, ac); load4(p + a.Fp, ok, gc);
     s[r] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < kFwdCh; ++i) {
       const float ya = wa[i][0] * a2[i] + wa[i][1] * a1[i] + wa[i][2] * ac[i];
       const float yg = wg[i][0] * g2[i] + wg[i][1] * g1[i] + wg[i][2] * gc[i];
       hv[r][i] = gelu_erf(yg) * ya;
@@ -146,36 +163,41 @@ ffn_mid_fwd_kernel(const MidArgs a, __nv_bfloat16* __restrict__ hn, float2* __re
     q[r] = 0.f;
     if (live) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { const float d = hv[r][i] - mean[r]; q[r] += d * d; }
+      for (int i = 0; i < kFwdCh; ++i) { const float d = hv[r][i] - mean[r]; q[r] += d * d; }
     }
   }
   block_sum_rows(q, red);
-  float gm[8];
+  float gm[kFwdCh];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) gm[i] = live ? a.gamma[c0 + i] : 0.f;
+  for (int i = 0; i < kFwdCh; ++i) gm[i] = live ? a.gamma[c0 + i] : 0.f;
   const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
   const uint32_t thresh = static_cast<uint32_t>(a.drop_p * 65536.f);
   const unsigned long long seed = (a.drop_p > 0.f) ? *a.seed : 0ull;
 #pragma unroll
   for (int r = 0; r < kT; ++r) {
-    if (t0 + r >= a.N) break;
+    if (t0 + r >= a.N) break;            // uniform across the block
     // padded channels are 0, each contributed (0-mean)^2 to q: remove them
     const float var = (q[r] - (a.Fp - a.F) * mean[r] * mean[r]) / a.F;
     const float rstd = rsqrtf(var + 1e-5f);
     const long long row = row_base + t0 + r;
     if (threadIdx.x == 0) stats[row] = make_float2(mean[r], rstd);
-    if (live) {
-      float o[8];
+    float o[kFwdCh];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = (hv[r][i] - mean[r]) * rstd * gm[i];
-      if (a.drop_p > 0.f) {
-        bool keep[8];
-        dropout_keep8(seed, a.layer, row, chunk, thresh, keep);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = keep[i] ? o[i] * keep_scale : 0.f;
-      }
-      store8(hn + row * a.Fp + c0, o);
+    for (int i = 0; i < kFwdCh; ++i) o[i] = (hv[r][i] - mean[r]) * rstd * gm[i];
+    if (a.drop_p > 0.f) {
+      // one Philox call per 8-channel chunk: the even lane of each pair computes it, the odd lane borrows the upper half
+      uint4 rnd = make_uint4(0, 0, 0, 0);
+      if (sub == 0) rnd = philox4x32(static_cast<uint32_t>(row), static_cast<uint32_t>(row >> 32), static_cast<uint32_t>(chunk8), a.layer,
+                                     static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+      const uint32_t z = __shfl_sync(0xffffffffu, rnd.z, threadIdx.x & 30);
+      const uint32_t w = __shfl_sync(0xffffffffu, rnd.w, threadIdx.x & 30);
+      const uint32_t r01 = sub ? z : rnd.x, r23 = sub ? w : rnd.y;
+      o[0] = (r01 & 0xffffu) >= thresh ? o[0] * keep_scale : 0.f;
+      o[1] = (r01 >> 16) >= thresh ? o[1] * keep_scale : 0.f;
+      o[2] = (r23 & 0xffffu) >= thresh ? o[2] * keep_scale : 0.f;
+      o[3] = (r23 >> 16) >= thresh ? o[3] * keep_scale : 0.f;
     }
+    if (live) store4(hn + row * a.Fp + c0, o);
   }
 }
 
@@ -219,18 +241,6 @@ ffn_mid_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dhn, const __nv_bfloa
   }
   s1 = warp_sum(s1); s2 = warp_sum(s2);
   if (lane == 0) rowstat[row] = make_float2(s1 / F, s2 / F);
-}
-
-__device__ __forceinline__ void load4(const __nv_bfloat16* p, bool ok, float (&f)[4]) {
-  uint2 raw = make_uint2(0, 0);
-  if (ok) raw = *reinterpret_cast<const uint2*>(p);
-  const float2 a = unpack_bf16x2(raw.x), b = unpack_bf16x2(raw.y);
-  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
-}
-__device__ __forceinline__ void store4(__nv_bfloat16* p, const float (&f)[4]) {
-  uint2 o;
-  o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-  *reinterpret_cast<uint2*>(p) = o;
 }
 
 constexpr int kWalkThreads = 128;
@@ -335,7 +345,7 @@ ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, 
   }
 }
 
-static int mid_threads(int Fp) { return ((Fp / 8 + 31) / 32) * 32; }
+static int mid_threads(int Fp) { return ((Fp / kFwdCh + 31) / 32) * 32; }
 
 }  // namespace omlm
 
@@ -345,7 +355,7 @@ int omlm_ffn_mid_fwd(const void* u, const float* conv_w, const float* gamma, voi
                      int N, int F, int Fp, float drop_p, const unsigned long long* seed, int layer,
                      void* stream) {
   using namespace omlm;
-  OMLM_CHECK_ARG(B > 0 && N > 0 && F > 0 && Fp >= F && Fp % 8 == 0 && Fp <= 8 * kMidMaxThreads, "ffn_mid_fwd: bad shape F=%d Fp=%d", F, Fp);
+  OMLM_CHECK_ARG(B > 0 && N > 0 && F > 0 && Fp >= F && Fp % 8 == 0 && Fp <= kFwdCh * kFwdMaxThreads, "ffn_mid_fwd: bad shape F=%d Fp=%d", F, Fp);
   OMLM_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || seed != nullptr), "ffn_mid_fwd: bad dropout args");
   MidArgs a{reinterpret_cast<const __nv_bfloat16*>(u), conv_w, gamma, N, F, Fp, drop_p, seed, static_cast<uint32_t>(layer)};
   const int slabs = (N + kT - 1) / kT;

@@ -103,6 +103,10 @@ int omlm_arange_f32(float* out, int n, void* stream);
 int omlm_attn_fwd(const void* qn, const void* kvn, const float* table, int table_ld,
                   const unsigned char* key_mask, void* out, float* lse2, int B, int N, int heads,
                   float scale, void* stream);
+/* Same contract on the tcgen05/TMEM/TMA path (two 128-row tiles per CTA, softmax warpgroups ping-ponged). */
+int omlm_attn_fwd_tc(const void* qn, const void* kvn, const float* table, int table_ld,
+                     const unsigned char* key_mask, void* out, float* lse2, int B, int N, int heads,
+                     float scale, void* stream);
 /* Accumulates (+=) into dqn fp32 [B,N,heads*64], dkvn fp32 [B,N,128], dtable fp32 [heads,table_ld]. */
 int omlm_attn_bwd(const void* qn, const void* kvn, const void* d_o, const void* o, const float* lse2,
                   const float* table, int table_ld, const unsigned char* key_mask, float* dsum_scratch,

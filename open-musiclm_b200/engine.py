@@ -281,7 +281,7 @@ class Engine:
             lib.gemm(ws["xn"][i], pk["wq"], ws["q_raw"][i], block_n=self._bn_for(M, HD, d))
             lib.gemm(ws["xraw"][i], pk["wkv"], ws["kv_raw"][i], block_n=128)
             lib.qk_l2norm_fwd(ws["q_raw"][i], ws["kv_raw"][i], pv[p + "0.q_scale"], pv[p + "0.k_scale"], ws["qn"][i], ws["kvn"][i], h)
-            lib.attn_fwd(ws["qn"][i], ws["kvn"][i], ws["table"], key_mask, ws["o"][i], ws["lse"][i], B, N, h)
+            lib.attn_fwd_tc(ws["qn"][i], ws["kvn"][i], ws["table"], key_mask, ws["o"][i], ws["lse"][i], B, N, h)
             lib.gemm(ws["o"][i], pk["wo"], xm, addend=xa, block_n=self._bn_for(M, d, HD))
             lib.layernorm_fwd(xm, pv[p + "2.0.gamma"], ws["xn2"][i], None, ws["st_f"][i])
             lib.gemm(ws["xn2"][i], pk["w1"], ws["u"][i], block_n=self._bn_for(M, 2 * Fp, d))

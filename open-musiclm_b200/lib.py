@@ -191,6 +191,11 @@ def attn_fwd(qn, kvn, table, key_mask, out, lse2, B, N, heads, scale=8.0):
          _I(B), _I(N), _I(heads), _F(scale), _stream())
 
 
+def attn_fwd_tc(qn, kvn, table, key_mask, out, lse2, B, N, heads, scale=8.0):
+    call("omlm_attn_fwd_tc", _p(qn), _p(kvn), _p(table), _I(table.stride(0)), _p(key_mask), _p(out), _p(lse2),
+         _I(B), _I(N), _I(heads), _F(scale), _stream())
+
+
 def attn_bwd(qn, kvn, d_o, o, lse2, table, key_mask, dsum_scratch, dqn, dkvn, dtable, B, N, heads, scale=8.0):
     call("omlm_attn_bwd", _p(qn), _p(kvn), _p(d_o), _p(o), _p(lse2), _p(table), _I(table.stride(0)), _p(key_mask),
          _p(dsum_scratch), _p(dqn), _p(dkvn), _p(dtable), _I(B), _I(N), _I(heads), _F(scale), _stream())

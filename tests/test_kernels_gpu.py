@@ -202,6 +202,12 @@ def test_attention_fwd_bwd(lib, B, N, h):
     out = torch.empty(M, h * 64, device=DEV, dtype=torch.bfloat16)
     lse2 = torch.empty(B, N * h, device=DEV)
     lib.attn_fwd(qn, kvn, table, key_mask, out, lse2, B, N, h)
+    out_tc = torch.full((M, h * 64), float("nan"), device=DEV, dtype=torch.bfloat16)
+    lse_tc = torch.full((B, N * h), float("nan"), device=DEV)
+    lib.attn_fwd_tc(qn, kvn, table, key_mask, out_tc, lse_tc, B, N, h)
+    torch.cuda.synchronize()
+    assert rel(out_tc, out) < 6e-3, rel(out_tc, out)
+    assert float((lse_tc - lse2).abs().max()) < 2e-2
     qf = qn.float().requires_grad_(True); kvf = kvn.float().requires_grad_(True); tf = table.clone().requires_grad_(True)
     ref = _attn_ref(qf, kvf, tf, key_mask, B, N, h)
     assert rel(out, ref.detach().reshape(M, -1)) < 6e-3
@@ -300,3 +306,25 @@ def test_adamw_matches_torch(lib):
         lib.adamw_step(p, g, m, v, n_decay, hyper, acc)
         ref = torch.cat([pa.detach().reshape(-1), pb.detach()])
         assert rel(p, ref) < 1e-6
+
+
+def test_attention_fwd_speed(lib):
+    """Prints the two forward attention paths side by side at the cfg2 shape (not a benchmark)."""
+    B, N, h = 16, 1024, 8
+    M = B * N
+    torch.manual_seed(0)
+    qn = F.normalize(torch.randn(M, h, 64, device=DEV), dim=-1).reshape(M, h * 64).bfloat16()
+    kvn = torch.randn(M, 128, device=DEV).bfloat16()
+    table = (torch.randn(h, 1, device=DEV) * 0.05 * torch.arange(N, device=DEV)[None]).contiguous()
+    key_mask = (torch.rand(B, N, device=DEV) > 0.15).to(torch.uint8); key_mask[:, 0] = 1
+    out = torch.empty(M, h * 64, device=DEV, dtype=torch.bfloat16); lse2 = torch.empty(B, N * h, device=DEV)
+    for name, fn in (("mma.sync", lib.attn_fwd), ("tcgen05", lib.attn_fwd_tc)):
+        for _ in range(3):
+            fn(qn, kvn, table, key_mask, out, lse2, B, N, h)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            fn(qn, kvn, table, key_mask, out, lse2, B, N, h)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"attn fwd {name}: {ms:.3f} ms  {B * N * h * 64 * (N + 1) * 2 / ms / 1e9:.0f} TFLOP/s (causal flops)")

@@ -26,7 +26,7 @@ from .model import TokenConditionedTransformer
 class HotPathTrainer:
     def __init__(self, transformer: TokenConditionedTransformer, *, cross_entropy_loss_weights: Optional[List[float]] = None,
                  lr=3e-4, lr_warmup=0, wd=0., max_grad_norm=0.5, grad_accum_every=1, mask_prob=0.15,
-                 betas=(0.9, 0.99), eps=1e-8, pad_id=-1, seed=0, process_group=None):
+                 betas=(0.9, 0.99), eps=1e-8, pad_id=-1, seed=0, process_group=None, use_cuda_graph=True):
         self.transformer = transformer
         self.eng = transformer.engine
         eng = self.eng
@@ -48,6 +48,9 @@ class HotPathTrainer:
         self.hyper = torch.zeros(9, dtype=torch.float32, device=eng.dev)
         self.loss_buf = torch.zeros(grad_accum_every, device=eng.dev)
         self._mask_draws = 0
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs = {}
+        self.loss_out = torch.zeros((), device=eng.dev)
         eng.arena_g.zero_()
 
     # -------------------------------------------------------------------------------------------
@@ -110,26 +113,64 @@ class HotPathTrainer:
         h[8] = 1.0 / self.world
         self.hyper.copy_(h, non_blocking=True)
 
-    def train_step(self, micro_batches: Sequence[Sequence[torch.Tensor]]):
-        """One optimiser step over `grad_accum_every` micro-batches (each a tuple of token-id tensors in
-        the stage's order, e.g. (clap, semantic, coarse)).  Returns the mean loss as a device scalar."""
-        assert len(micro_batches) == self.grad_accum_every
+    def _step_body(self, micro_batches):
+        """Everything of one optimiser step that runs on the device (capturable in a CUDA graph)."""
         eng = self.eng
-        self.transformer.train()
         eng.seed += 1
         for i, mb in enumerate(micro_batches):
             self._micro_batch(mb, True, i, True)
         if self.world > 1:
             dist.all_reduce(eng.arena_g, op=dist.ReduceOp.SUM, group=self.pg)
-        self._set_hyper()
         eng.sumsq.zero_()
         if self.max_grad_norm is not None:
             lib.grad_sumsq(eng.arena_g, eng.sumsq, prescale=1.0 / self.world)
         lib.adamw_step(eng.arena_p, eng.arena_g, eng.adam_m, eng.adam_v, eng.n_decay, self.hyper, eng.sumsq)
         eng.arena_g.zero_()
         eng.refresh_packed(force=True)
+        self.loss_out.copy_(self.loss_buf.sum() / self.grad_accum_every)
+
+    def train_step(self, micro_batches: Sequence[Sequence[torch.Tensor]]):
+        """One optimiser step over `grad_accum_every` micro-batches (each a tuple of token-id tensors in
+        the stage's order, e.g. (clap, semantic, coarse); host or device).  Returns the mean loss as a device
+        scalar.  After two eager steps per input shape the whole step (~250 kernels) is replayed from a CUDA graph:
+        inputs are copied into static device buffers, hyper-parameters live in device memory."""
+        assert len(micro_batches) == self.grad_accum_every
+        eng = self.eng
+        self.transformer.train()
+        self._set_hyper()
+        if not self.use_cuda_graph:
+            self._step_body(micro_batches)
+            self.steps += 1
+            return self.loss_out
+        key = tuple(tuple(t.shape) for mb in micro_batches for t in mb)
+        st = self._graphs.get(key)
+        if st is None:
+            st = self._graphs[key] = dict(count=0, graph=None, static=[
+                [torch.empty(tuple(t.shape), dtype=torch.int64, device=eng.dev) for t in mb] for mb in micro_batches])
+        for mb, smb in zip(micro_batches, st["static"]):
+            for t, sbuf in zip(mb, smb):
+                sbuf.copy_(t, non_blocking=True)
+        if st["graph"] is not None:
+            st["graph"].replay()
+        elif st["count"] < 2:
+            self._step_body(st["static"])
+            st["count"] += 1
+        else:
+            torch.cuda.synchronize()
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._step_body(st["static"])
+                st["graph"] = g
+                g.replay()
+            except Exception as e:  # capture not possible in this environment: stay on the eager launch path (same kernels)
+                import warnings
+                warnings.warn(f"CUDA graph capture of the training step failed ({e}); continuing with eager launches")
+                self.use_cuda_graph = False
+                torch.cuda.synchronize()
+                self._step_body(st["static"])
         self.steps += 1
-        return self.loss_buf.sum() / self.grad_accum_every
+        return self.loss_out
 
     @torch.no_grad()
     def eval_loss(self, token_ids: Sequence[torch.Tensor]):

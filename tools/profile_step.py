@@ -25,7 +25,7 @@ def main():
     args = ap.parse_args()
     torch.manual_seed(0)
     model = O.create_coarse_transformer(**bench.CFG).cuda()
-    tr = O.HotPathTrainer(model, cross_entropy_loss_weights=bench.TRAIN["ce_weights"], lr=3e-4, lr_warmup=6000, wd=0.01)
+    tr = O.HotPathTrainer(model, cross_entropy_loss_weights=bench.TRAIN["ce_weights"], lr=3e-4, lr_warmup=6000, wd=0.01, use_cuda_graph=False)
     gen = torch.Generator().manual_seed(1234)
     batch = [t.cuda() for t in bench.synth_batch(args.batch, gen)]
     for _ in range(3):

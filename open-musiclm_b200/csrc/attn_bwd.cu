@@ -206,10 +206,6 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qn, const __nv_bfloat16* __res
         const float da = pa * (dp[n][e] - dsm), db = pb * (dp[n][2 + e] - dsm);
         s[n][e] = pa; s[n][2 + e] = pb;
         dp[n][e] = da; dp[n][2 + e] = db;
-        // dTable[hh, i - j] += dS  (delta = di + i_min - j)
-        const int dA = di + i_min - (j0 + key_a), dB = di + i_min - (j0 + key_b);
-        if (da != 0.f) atomicAdd(&sm.dbias[hh * kDbW + (dA & (kDbW - 1))], da);
-        if (db != 0.f) atomicAdd(&sm.dbias[hh * kDbW + (dB & (kDbW - 1))], db);
       }
       pf[n][0] = pack_bf16x2(s[n][0], s[n][1]);   pf[n][1] = pack_bf16x2(s[n][2], s[n][3]);
       dsf[n][0] = pack_bf16x2(dp[n][0], dp[n][1]); dsf[n][1] = pack_bf16x2(dp[n][2], dp[n][3]);
@@ -232,6 +228,27 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qn, const __nv_bfloat16* __res
       }
     }
     __syncthreads();  // dS tile complete
+    // ---- dTable[hh, i-j] += dS: every (head, delta) bin of this tile has ONE owner thread that sums its diagonal
+    // (<= positions-per-tile elements of the bf16 dS^T tile) and updates the circular window without atomics.
+    {
+      const int P = i_max - i_min + 1;
+      for (int idx = threadIdx.x; idx < h * W; idx += kBwdThreads) {
+        const int hh = idx / W, w = idx - hh * W;
+        const int delta = delta_min + w;
+        if (delta < 0) continue;
+        float acc = 0.f;
+        for (int p = 0; p < P; ++p) {
+          const int i = i_min + p;
+          const int kl = i - delta - j0;            // local key
+          const int rl = i * h + hh - r0;           // local row
+          if (kl >= 0 && kl < kBKV && rl >= 0 && rl < kBQ) {
+            const __nv_bfloat16 v = *reinterpret_cast<const __nv_bfloat16*>(sm.ds + tile_off(kl, rl >> 3) + (rl & 7) * 2);
+            acc += __bfloat162float(v);
+          }
+        }
+        sm.dbias[hh * kDbW + (delta & (kDbW - 1))] += acc;
+      }
+    }
     // ---- dQ[64 rows x 64 d] += dS K : warp w -> rows 16*(w&3).., d half (w>>2)*32, k over the 128 keys
     {
       const int m0 = (warp & 3) * 16, n0 = (warp >> 2) * 32;

@@ -20,13 +20,14 @@ constexpr int kBKV = 128;   // keys per CTA
 constexpr int kBwdThreads = 256;
 constexpr int kDbW = 256;   // circular dbias window per head
 constexpr int kBwdMaxHeads = 16;
+constexpr int kDsPad = 64;  // zero key-rows in front of the dS^T tile (>= positions per 64-row tile - 1)
 
 struct AttnBwdSmem {
   uint8_t k[kBKV * 128];
   uint8_t v[kBKV * 128];
   uint8_t q[2][kBQ * 128];
   uint8_t d_o[2][kBQ * 128];
-  uint8_t ds[kBKV * 128];      // dS^T as [key][row] bf16
+  uint8_t ds[(kDsPad + kBKV + 80) * 128];   // [64 zero rows | dS^T as [key][row] bf16 | 80 zero rows]: guard bands for the diagonal MMA
   float lse[2][kBQ];
   float dsum[2][kBQ];
   int rowinfo[kBQ];
@@ -107,6 +108,8 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qn, const __nv_bfloat16* __res
     sm.kneg[threadIdx.x] = vis ? 0.f : -INFINITY;
   }
   for (int i = threadIdx.x; i < kBwdMaxHeads * kDbW; i += kBwdThreads) sm.dbias[i] = 0.f;
+  for (int i = threadIdx.x; i < kDsPad * 32; i += kBwdThreads) reinterpret_cast<uint32_t*>(sm.ds)[i] = 0u;
+  for (int i = threadIdx.x; i < 80 * 32; i += kBwdThreads) reinterpret_cast<uint32_t*>(sm.ds + (kDsPad + kBKV) * 128)[i] = 0u;
   auto load_q = [&](int rt, int buf) {
     const int r0 = rt * kBQ;
     const uint32_t sq = smem_u32(sm.q[buf]), sdo = smem_u32(sm.d_o[buf]);
@@ -210,8 +213,8 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qn, const __nv_bfloat16* __res
       pf[n][0] = pack_bf16x2(s[n][0], s[n][1]);   pf[n][1] = pack_bf16x2(s[n][2], s[n][3]);
       dsf[n][0] = pack_bf16x2(dp[n][0], dp[n][1]); dsf[n][1] = pack_bf16x2(dp[n][2], dp[n][3]);
       // dS^T to smem as [key][row]: rows 2t,2t+1 of chunk n
-      *reinterpret_cast<uint32_t*>(sm.ds + tile_off(key_a, n) + t * 4) = dsf[n][0];
-      *reinterpret_cast<uint32_t*>(sm.ds + tile_off(key_b, n) + t * 4) = dsf[n][1];
+      *reinterpret_cast<uint32_t*>(sm.ds + tile_off(key_a + kDsPad, n) + t * 4) = dsf[n][0];
+      *reinterpret_cast<uint32_t*>(sm.ds + tile_off(key_b + kDsPad, n) + t * 4) = dsf[n][1];
     }
     // ---- dV += P^T dO ;  dK += dS^T Q    (k = 64 rows of the tile)
 #pragma unroll
@@ -228,25 +231,43 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qn, const __nv_bfloat16* __res
       }
     }
     __syncthreads();  // dS tile complete
-    // ---- dTable[hh, i-j] += dS: every (head, delta) bin of this tile has ONE owner thread that sums its diagonal
-    // (<= positions-per-tile elements of the bf16 dS^T tile) and updates the circular window without atomics.
+    // ---- dTable[hh, i-j] += dS on the tensor cores.  For position p of this tile the rows r = (p, hh) of dS^T
+    // [key][row] contribute dS^T[key][r] to bin delta = i_min + p - key.  Shifting the tile DOWN by p key-rows
+    // (free: ldmatrix takes per-row addresses) aligns every position on delta = i_min - j0 - k', so
+    //     out[k'][hh] = sum_p  dS^T[k' + p][:] . E_p[:, hh],   E_p[r][hh] = [row r is (position p, head hh)]
+    // is a sum of small MMAs with 0/1 B fragments built from rowinfo.  Each (k', hh) bin then has one owner thread.
     {
       const int P = i_max - i_min + 1;
-      for (int idx = threadIdx.x; idx < h * W; idx += kBwdThreads) {
-        const int hh = idx / W, w = idx - hh * W;
-        const int delta = delta_min + w;
-        if (delta < 0) continue;
-        float acc = 0.f;
-        for (int p = 0; p < P; ++p) {
-          const int i = i_min + p;
-          const int kl = i - delta - j0;            // local key
-          const int rl = i * h + hh - r0;           // local row
-          if (kl >= 0 && kl < kBKV && rl >= 0 && rl < kBQ) {
-            const __nv_bfloat16 v = *reinterpret_cast<const __nv_bfloat16*>(sm.ds + tile_off(kl, rl >> 3) + (rl & 7) * 2);
-            acc += __bfloat162float(v);
+      const int n_heads_tiles = (h + 7) >> 3;
+      for (int mt = warp; mt < (kDsPad + kBKV) / 16; mt += 8) {      // output rows k' = kb0 .. kb0+15, k' in [-64, 127]
+        const int kb0 = mt * 16 - kDsPad;
+        if (kb0 + 15 < -(P - 1)) continue;                             // no position can reach these rows
+        for (int nt = 0; nt < n_heads_tiles; ++nt) {
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int p = 0; p < P; ++p) {
+            const int rbase = (i_min + p) * h - r0;                    // local row of (position p, head 0)
+            const int lo = max(0, rbase), hi = min(kBQ, rbase + h);
+            if (lo >= hi) continue;
+            for (int ks = lo >> 4; ks <= (hi - 1) >> 4; ++ks) {
+              // B fragment (k = tile row, n = head), built arithmetically: 1.0 where row is (position p, head g + 8 nt)
+              const int want = rbase + g + 8 * nt;                     // the one local row that carries this head at position p
+              const int ra = ks * 16 + 2 * t;
+              const bool okh = (g + 8 * nt) < h;
+              const uint32_t b0 = (okh && ra == want ? 0x3F80u : 0u) | (okh && ra + 1 == want ? 0x3F800000u : 0u);
+              const uint32_t b1 = (okh && ra + 8 == want ? 0x3F80u : 0u) | (okh && ra + 9 == want ? 0x3F800000u : 0u);
+              uint32_t af[4];
+              load_a_frag(sds, kb0 + kDsPad + p, ks, lane, af);      // rows (k' + p) of dS^T, shifted by the position
+              mma_bf16(acc, af[0], af[1], af[2], af[3], b0, b1);
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int kp = kb0 + g + (e >> 1) * 8;
+            const int hh = nt * 8 + 2 * t + (e & 1);
+            const int delta = i_min - j0 - kp;
+            if (hh < h && delta >= 0 && acc[e] != 0.f) sm.dbias[hh * kDbW + (delta & (kDbW - 1))] += acc[e];
           }
         }
-        sm.dbias[hh * kDbW + (delta & (kDbW - 1))] += acc;
       }
     }
     // ---- dQ[64 rows x 64 d] += dS K : warp w -> rows 16*(w&3).., d half (w>>2)*32, k over the 128 keys
@@ -258,7 +279,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qn, const __nv_bfloat16* __res
 #pragma unroll
       for (int kk = 0; kk < 8; ++kk) {
         uint32_t af[4];
-        load_a_frag_t(sds, kk * 16, m0, lane, af);
+        load_a_frag_t(sds, kk * 16 + kDsPad, m0, lane, af);
 #pragma unroll
         for (int np = 0; np < 2; ++np) {
           uint32_t bk[4];

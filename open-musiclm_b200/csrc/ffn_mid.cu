@@ -252,9 +252,10 @@ ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, 
   const int slabs = (a.N + rows_per_cta - 1) / rows_per_cta;
   const int b = blockIdx.x / slabs, t0 = (blockIdx.x - b * slabs) * rows_per_cta;
   const int t_end = min(a.N, t0 + rows_per_cta);
-  const int c0 = (blockIdx.y * kWalkThreads + threadIdx.x) * 4;
-  if (c0 >= a.Fp) return;
-  const int chunk8 = c0 >> 3, sub = (c0 >> 2) & 1;  // dropout bits are defined per 8-channel chunk
+  const int c0raw = (blockIdx.y * kWalkThreads + threadIdx.x) * 4;
+  const bool active = c0raw < a.Fp;                  // inactive lanes stay alive for the pair shuffles below
+  const int c0 = active ? c0raw : 0;
+  const int chunk8 = c0 >> 3, sub = threadIdx.x & 1;  // dropout bits are defined per 8-channel chunk (one lane pair)
   const long long row_base = static_cast<long long>(b) * a.N;
   const long ld = 2L * a.Fp;
   float wa[4][3], wg[4][3], gm[4];
@@ -284,7 +285,7 @@ ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, 
     for (int k = 0; k < 3; ++k) { dwa[i][k] = 0.f; dwg[i][k] = 0.f; } }
 
   for (int tp = t0; tp < t_end + 2; ++tp) {
-    const bool valid = tp < a.N;
+    const bool valid = active && tp < a.N;
     const bool own = tp < t_end;                 // rows >= t_end are the next slab's: recomputed here only for the conv halo
     const long long row = row_base + tp;
     float ua0[4], ug0[4], d[4];
@@ -293,11 +294,18 @@ ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, 
     load4(dhn + row * a.Fp + c0, valid, d);
     float2 st = make_float2(0.f, 0.f), rs = make_float2(0.f, 0.f);
     if (valid) { st = stats[row]; rs = rowstat[row]; }
-    if (a.drop_p > 0.f && valid) {
-      bool keep[8];
-      dropout_keep8(seed, a.layer, row, chunk8, thresh, keep);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) d[i] = keep[sub * 4 + i] ? d[i] * keep_scale : 0.f;
+    if (a.drop_p > 0.f) {
+      // one Philox call per 8-channel chunk: the even lane computes it, the odd lane borrows the upper 64 bits
+      uint4 rnd = make_uint4(0, 0, 0, 0);
+      if (sub == 0) rnd = philox4x32(static_cast<uint32_t>(row), static_cast<uint32_t>(row >> 32), static_cast<uint32_t>(chunk8), a.layer,
+                                     static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+      const uint32_t z = __shfl_sync(0xffffffffu, rnd.z, threadIdx.x & 30);
+      const uint32_t w = __shfl_sync(0xffffffffu, rnd.w, threadIdx.x & 30);
+      const uint32_t r01 = sub ? z : rnd.x, r23 = sub ? w : rnd.y;
+      d[0] = (r01 & 0xffffu) >= thresh ? d[0] * keep_scale : 0.f;
+      d[1] = (r01 >> 16) >= thresh ? d[1] * keep_scale : 0.f;
+      d[2] = (r23 & 0xffffu) >= thresh ? d[2] * keep_scale : 0.f;
+      d[3] = (r23 >> 16) >= thresh ? d[3] * keep_scale : 0.f;
     }
     float da0[4], dg0[4];
 #pragma unroll
@@ -318,7 +326,7 @@ ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, 
         dwg[i][0] += dg0[i] * ug2[i]; dwg[i][1] += dg0[i] * ug1[i]; dwg[i][2] += dg0[i] * ug0[i];
       }
     }
-    if (tp - 2 >= t0) {  // du[t'-2] = w2 dy[t'-2] + w1 dy[t'-1] + w0 dy[t']
+    if (active && tp - 2 >= t0) {  // du[t'-2] = w2 dy[t'-2] + w1 dy[t'-1] + w0 dy[t']
       float oa[4], og[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -334,6 +342,7 @@ ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, 
       da2[i] = da1[i]; da1[i] = da0[i]; dg2[i] = dg1[i]; dg1[i] = dg0[i];
     }
   }
+  if (!active) return;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     atomicAdd(&dgamma[c0 + i], dgam[i]);

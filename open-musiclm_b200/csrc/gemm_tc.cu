@@ -171,8 +171,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
       const int tile = w / splits;
       const int n_blk = tile % n_tiles, m_blk = tile / n_tiles;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
       int row = m_blk * BM + quarter * 32 + lane;
       bool row_ok = row < M;
       if (ep.row_split > 0) {
@@ -181,10 +179,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         row = half * ep.row_valid + r;
       }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+      // residual / beta=1 addend: software-pipelined one 32-column chunk ahead so that its HBM latency overlaps
+      // the TMEM load + store of the previous chunk (and, for chunk 0, the tail of the tile's MMAs)
+      const bool pf = row_ok && ep.addend != nullptr && ep.vec_ok;
+      float4 nxt[8];
+      auto prefetch = [&](int c) {
+        const int col0 = n_blk * BN + c * 32;
+        if (pf && c < BN / 32 && col0 + 32 <= ep.n_valid) {
+          const float4* ap = reinterpret_cast<const float4*>(ep.addend + static_cast<long>(row) * ep.ldadd + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) nxt[j] = ap[j];
+        }
+      };
+      prefetch(0);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
+        float4 cur[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+        prefetch(c + 1);
         tmem_ld_wait();
         const int col0 = n_blk * BN + c * 32;
         if (row_ok && col0 < ep.n_valid) {
@@ -193,14 +210,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
           const bool full = (col0 + 32 <= ep.n_valid) && ep.vec_ok;
           if (ep.addend != nullptr) {
-            const float* ap = ep.addend + static_cast<long>(row) * ep.ldadd + col0;
             if (full) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 a4 = reinterpret_cast<const float4*>(ap)[j];
-                v[4 * j] += a4.x; v[4 * j + 1] += a4.y; v[4 * j + 2] += a4.z; v[4 * j + 3] += a4.w;
+                v[4 * j] += cur[j].x; v[4 * j + 1] += cur[j].y; v[4 * j + 2] += cur[j].z; v[4 * j + 3] += cur[j].w;
               }
             } else {
+              const float* ap = ep.addend + static_cast<long>(row) * ep.ldadd + col0;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (col0 + j < ep.n_valid) v[j] += ap[j];

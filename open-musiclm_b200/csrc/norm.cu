@@ -67,10 +67,12 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
 
 // ------------------------------------------------------------------------------------------------
 // LayerNorm backward.  dx = [dres] + [draw] + rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat))
-// dgamma[col] += sum_rows dy * xhat  (fp32 atomics, one per column per block).
+// dgamma[col] += sum_rows dy * xhat  (fp32; per-block partials in smem, one global atomic per column per block).
 // dy rows may be permuted (src_row: row of dy for this x row, -1 = no gradient).
+// Two passes per row with a re-read (the 6 KB row is L1-resident) instead of caching xhat / g*dy in registers:
+// ~64 registers per thread -> 4 blocks (32 warps) per SM, which is what hides the HBM latency here.
 template <int NCHUNK>
-__global__ void __launch_bounds__(kNormThreads)
+__global__ void __launch_bounds__(kNormThreads, 3)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
                      const float2* __restrict__ stats, const float* __restrict__ gamma,
                      const float* __restrict__ dres, const __nv_bfloat16* __restrict__ draw,
@@ -91,23 +93,23 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
     const float* xr = x + static_cast<long long>(row) * D;
     long long drow = row;
     if (src_row != nullptr) drow = src_row[row];
-    float4 gd[NCHUNK], xh[NCHUNK];
+    const __nv_bfloat16* dyr = dy + (drow < 0 ? 0 : drow) * D;
     float s1 = 0.f, s2 = 0.f;
+    if (drow >= 0) {
 #pragma unroll
-    for (int c = 0; c < NCHUNK; ++c) {
-      const int col = (c * 32 + lane) * 4;
-      gd[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-      xh[c] = gd[c];
-      if (col < D && drow >= 0) {
-        const float4 xv = *reinterpret_cast<const float4*>(xr + col);
-        const uint2 dv = *reinterpret_cast<const uint2*>(dy + drow * D + col);
-        const float4 g = *reinterpret_cast<const float4*>(gamma + col);
-        const float2 d01 = unpack_bf16x2(dv.x), d23 = unpack_bf16x2(dv.y);
-        xh[c] = make_float4((xv.x - st.x) * st.y, (xv.y - st.x) * st.y, (xv.z - st.x) * st.y, (xv.w - st.x) * st.y);
-        dg[c].x += d01.x * xh[c].x; dg[c].y += d01.y * xh[c].y; dg[c].z += d23.x * xh[c].z; dg[c].w += d23.y * xh[c].w;
-        gd[c] = make_float4(d01.x * g.x, d01.y * g.y, d23.x * g.z, d23.y * g.w);
-        s1 += gd[c].x + gd[c].y + gd[c].z + gd[c].w;
-        s2 += gd[c].x * xh[c].x + gd[c].y * xh[c].y + gd[c].z * xh[c].z + gd[c].w * xh[c].w;
+      for (int c = 0; c < NCHUNK; ++c) {
+        const int col = (c * 32 + lane) * 4;
+        if (col < D) {
+          const float4 xv = *reinterpret_cast<const float4*>(xr + col);
+          const uint2 dv = *reinterpret_cast<const uint2*>(dyr + col);
+          const float4 g = *reinterpret_cast<const float4*>(gamma + col);
+          const float2 d01 = unpack_bf16x2(dv.x), d23 = unpack_bf16x2(dv.y);
+          const float h0 = (xv.x - st.x) * st.y, h1 = (xv.y - st.x) * st.y, h2 = (xv.z - st.x) * st.y, h3 = (xv.w - st.x) * st.y;
+          dg[c].x += d01.x * h0; dg[c].y += d01.y * h1; dg[c].z += d23.x * h2; dg[c].w += d23.y * h3;
+          const float g0 = d01.x * g.x, g1 = d01.y * g.y, g2 = d23.x * g.z, g3 = d23.y * g.w;
+          s1 += g0 + g1 + g2 + g3;
+          s2 += g0 * h0 + g1 * h1 + g2 * h2 + g3 * h3;
+        }
       }
     }
     s1 = warp_sum(s1) / D;
@@ -116,11 +118,17 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
     for (int c = 0; c < NCHUNK; ++c) {
       const int col = (c * 32 + lane) * 4;
       if (col < D) {
-        float4 o;
-        o.x = st.y * (gd[c].x - s1 - xh[c].x * s2);
-        o.y = st.y * (gd[c].y - s1 - xh[c].y * s2);
-        o.z = st.y * (gd[c].z - s1 - xh[c].z * s2);
-        o.w = st.y * (gd[c].w - s1 - xh[c].w * s2);
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (drow >= 0) {
+          const float4 xv = *reinterpret_cast<const float4*>(xr + col);           // L1 hit
+          const uint2 dv = *reinterpret_cast<const uint2*>(dyr + col);
+          const float4 g = *reinterpret_cast<const float4*>(gamma + col);
+          const float2 d01 = unpack_bf16x2(dv.x), d23 = unpack_bf16x2(dv.y);
+          o.x = st.y * (d01.x * g.x - s1 - (xv.x - st.x) * st.y * s2);
+          o.y = st.y * (d01.y * g.y - s1 - (xv.y - st.x) * st.y * s2);
+          o.z = st.y * (d23.x * g.z - s1 - (xv.z - st.x) * st.y * s2);
+          o.w = st.y * (d23.y * g.w - s1 - (xv.w - st.x) * st.y * s2);
+        }
         if (dres != nullptr) {
           const float4 r = *reinterpret_cast<const float4*>(dres + static_cast<long long>(row) * D + col);
           o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
@@ -313,8 +321,8 @@ template <int NCHUNK>
 static int launch_ln_bwd(const __nv_bfloat16* dy, const float* x, const float2* stats, const float* gamma,
                          const float* dres, const __nv_bfloat16* draw, const int* src_row, float* dx,
                          __nv_bfloat16* dx_bf16, float* dgamma, int M, int D, cudaStream_t st) {
-  // ~4 blocks per SM; each block walks a contiguous slab of rows and flushes dgamma once.
-  int blocks = num_sms() * 4;
+  // ~2 waves of 3 resident blocks per SM; each block walks a contiguous slab of rows and flushes dgamma once.
+  int blocks = num_sms() * 6;
   int rows_per_block = (M + blocks - 1) / blocks;
   if (rows_per_block < 8) rows_per_block = 8;
   blocks = (M + rows_per_block - 1) / rows_per_block;

@@ -113,6 +113,12 @@ int omlm_attn_bwd(const void* qn, const void* kvn, const void* d_o, const void* 
                   float* dqn, float* dkvn, float* dtable, int B, int N, int heads, float scale,
                   void* stream);
 
+/* tcgen05/TMEM/TMA backward.  ds_scratch: bf16 [B, N*heads, round_up(N,128)] (dS tiles for the bias-gradient pass). */
+int omlm_attn_bwd_tc(const void* qn, const void* kvn, const void* d_o, const void* o, const float* lse2,
+                     const float* table, int table_ld, const unsigned char* key_mask, float* dsum_scratch,
+                     void* ds_scratch, float* dqn, float* dkvn, float* dtable, int B, int N, int heads,
+                     float scale, void* stream);
+
 /* ---- ConvFeedForward middle (transformer.py:122-150): conv k=3 -> GEGLU -> LN(F) -> dropout ----
  * u bf16 [B*N, 2Fp] (value half | gate half), conv_w fp32 [2Fp,3], gamma fp32 [Fp] (packed/padded)
  * -> hn bf16 [B*N, Fp], stats fp32 [B*N, 2]. */

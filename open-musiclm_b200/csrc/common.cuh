@@ -33,6 +33,10 @@ void set_last_error(const char* fmt, ...);
 int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t dim0, uint64_t dim1,
                       uint64_t pitch_bytes, uint32_t box0, uint32_t box1);
 
+// 3-D bf16 tensor map (dim0 contiguous), SWIZZLE_128B, box {box0, box1, 1}: out-of-range rows/planes are clipped.
+int make_tmap_bf16_3d(CUtensorMap* out, const void* gptr, uint64_t dim0, uint64_t dim1, uint64_t dim2,
+                      uint64_t pitch1_bytes, uint64_t pitch2_bytes, uint32_t box0, uint32_t box1);
+
 int num_sms();
 
 // ---- device math --------------------------------------------------------------------------

@@ -50,6 +50,24 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t dim0, uint64_
   return 0;
 }
 
+int make_tmap_bf16_3d(CUtensorMap* out, const void* gptr, uint64_t dim0, uint64_t dim1, uint64_t dim2,
+                      uint64_t pitch1_bytes, uint64_t pitch2_bytes, uint32_t box0, uint32_t box1) {
+  std::call_once(g_encode_once, resolve_encode);
+  OMLM_CHECK_ARG(g_encode != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  OMLM_CHECK_ARG((reinterpret_cast<uintptr_t>(gptr) & 15) == 0 && (pitch1_bytes & 15) == 0 && (pitch2_bytes & 15) == 0,
+                 "TMA 3-D map: base and pitches must be 16B aligned");
+  OMLM_CHECK_ARG(box0 * 2 == 128 && box1 >= 1 && box1 <= 256, "bad TMA box %u x %u", box0, box1);
+  cuuint64_t dims[3] = {dim0, dim1, dim2};
+  cuuint64_t strides[2] = {pitch1_bytes, pitch2_bytes};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(gptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  OMLM_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r);
+  return 0;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {

@@ -220,7 +220,7 @@ class Engine:
                 dlogits=[E(max(pl.B * c, 1), self.Cp[s]) for (s, qi, c, b0) in pl.groups],
                 dxf=E(max(pl.rows_total, 1), d), dx=[E(M, d, dt=f32) for _ in range(2)], dx_bf=E(M, d),
                 dhn=E(M, Fp), rowstat=E(M, 2, dt=f32), du=E(M, 2 * Fp), dxn=E(M, d), dxraw=E(M, d),
-                d_o=E(M, HD), dqn=E(M, HD, dt=f32), dkvn=E(M, 128, dt=f32), dsum=E(M * h, dt=f32),
+                d_o=E(M, HD), ds=E(pl.B, pl.N * h, _round_up(pl.N, 128)), dqn=E(M, HD, dt=f32), dkvn=E(M, 128, dt=f32), dsum=E(M * h, dt=f32),
                 dq_raw=E(M, HD), dkv_raw=E(M, 128), dtable=E(h, pl.N, dt=f32),
                 dgin=E(Fp, dt=f32), dconv=E(2 * Fp, 3, dt=f32),
                 rp_d0=E(pl.N, self.Hr, dt=f32), rp_d1=E(pl.N, self.Hr, dt=f32), rp_dz_bf=E(pl.N, self.Hr),
@@ -349,8 +349,8 @@ class Engine:
             lib.gemm(ws["dx_bf"], pk["wo"], ws["d_o"], b_mn=True, M=M, N=HD, K=d, block_n=self._bn_for(M, HD, d))
             self._wgrad(ws["dx_bf"], ws["o"][l], gv[p + "0.to_out.0.weight"], d, HD)
             ws["dqn"].zero_(); ws["dkvn"].zero_()
-            lib.attn_bwd(ws["qn"][l], ws["kvn"][l], ws["d_o"], ws["o"][l], ws["lse"][l], ws["table"], key_mask, ws["dsum"],
-                         ws["dqn"], ws["dkvn"], ws["dtable"], B, N, h)
+            lib.attn_bwd_tc(ws["qn"][l], ws["kvn"][l], ws["d_o"], ws["o"][l], ws["lse"][l], ws["table"], key_mask, ws["dsum"],
+                            ws["ds"], ws["dqn"], ws["dkvn"], ws["dtable"], B, N, h)
             lib.qk_l2norm_bwd(ws["dqn"], ws["dkvn"], ws["q_raw"][l], ws["kv_raw"][l], pv[p + "0.q_scale"], pv[p + "0.k_scale"],
                               ws["dq_raw"], ws["dkv_raw"], gv[p + "0.q_scale"], gv[p + "0.k_scale"], h)
             lib.gemm(ws["dq_raw"], pk["wq"], ws["dxn"], b_mn=True, M=M, N=d, K=HD, block_n=self._bn_for(M, d, HD))

@@ -201,6 +201,11 @@ def attn_bwd(qn, kvn, d_o, o, lse2, table, key_mask, dsum_scratch, dqn, dkvn, dt
          _p(dsum_scratch), _p(dqn), _p(dkvn), _p(dtable), _I(B), _I(N), _I(heads), _F(scale), _stream())
 
 
+def attn_bwd_tc(qn, kvn, d_o, o, lse2, table, key_mask, dsum_scratch, ds_scratch, dqn, dkvn, dtable, B, N, heads, scale=8.0):
+    call("omlm_attn_bwd_tc", _p(qn), _p(kvn), _p(d_o), _p(o), _p(lse2), _p(table), _I(table.stride(0)), _p(key_mask),
+         _p(dsum_scratch), _p(ds_scratch), _p(dqn), _p(dkvn), _p(dtable), _I(B), _I(N), _I(heads), _F(scale), _stream())
+
+
 def ffn_mid_fwd(u, conv_w, gamma, hn, stats, B, N, F, Fp, drop_p=0.0, seed=None, layer=0):
     call("omlm_ffn_mid_fwd", _p(u), _p(conv_w), _p(gamma), _p(hn), _p(stats), _I(B), _I(N), _I(F), _I(Fp),
          _F(drop_p), _p(seed), _I(layer), _stream())

@@ -220,6 +220,15 @@ def test_attention_fwd_bwd(lib, B, N, h):
     assert rel(dqn, qf.grad) < 1.5e-2
     assert rel(dkvn, kvf.grad) < 1.5e-2
     assert rel(dtab[:, :N], tf.grad[:, :N]) < 1.5e-2
+    # tcgen05 backward
+    dqn2 = torch.zeros(M, h * 64, device=DEV); dkvn2 = torch.zeros(M, 128, device=DEV); dtab2 = torch.zeros_like(table)
+    Ns = (N + 127) // 128 * 128
+    ds_scratch = torch.full((B, N * h, Ns), float("nan"), device=DEV, dtype=torch.bfloat16)
+    lib.attn_bwd_tc(qn, kvn, d_o, out, lse2, table, key_mask, dsum, ds_scratch, dqn2, dkvn2, dtab2, B, N, h)
+    torch.cuda.synchronize()
+    assert rel(dqn2, qf.grad) < 1.5e-2, rel(dqn2, qf.grad)
+    assert rel(dkvn2, kvf.grad) < 1.5e-2, rel(dkvn2, kvf.grad)
+    assert rel(dtab2[:, :N], tf.grad[:, :N]) < 1.5e-2, rel(dtab2[:, :N], tf.grad[:, :N])
 
 
 # ------------------------------------------------------------------------------------------------ FFN middle

@@ -18,3 +18,10 @@ e0.record()
 for _ in range(10): lib.attn_bwd(qn, kvn, d_o, out, lse, table, km, dsum, dqn, dkvn, dtab, B, N, h)
 e1.record(); torch.cuda.synchronize()
 print(f"attn_bwd: {e0.elapsed_time(e1)/10*1000:.1f} us")
+Ns = (N + 127) // 128 * 128
+ds = torch.empty(B, N * h, Ns, device="cuda", dtype=torch.bfloat16)
+for _ in range(3): lib.attn_bwd_tc(qn, kvn, d_o, out, lse, table, km, dsum, ds, dqn, dkvn, dtab, B, N, h)
+e0.record()
+for _ in range(10): lib.attn_bwd_tc(qn, kvn, d_o, out, lse, table, km, dsum, ds, dqn, dkvn, dtab, B, N, h)
+e1.record(); torch.cuda.synchronize()
+print(f"attn_bwd_tc: {e0.elapsed_time(e1)/10*1000:.1f} us")

@@ -244,23 +244,32 @@ ffn_mid_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dhn, const __nv_bfloa
 }
 
 constexpr int kWalkThreads = 128;
+constexpr int kWalkCh = 2;   // channels (of each GEGLU half) per thread: small footprint -> many resident warps
 
-__global__ void __launch_bounds__(kWalkThreads, 4)
+__device__ __forceinline__ void load2(const __nv_bfloat16* p, bool ok, float (&f)[2]) {
+  uint32_t raw = 0;
+  if (ok) raw = *reinterpret_cast<const uint32_t*>(p);
+  const float2 a = unpack_bf16x2(raw);
+  f[0] = a.x; f[1] = a.y;
+}
+
+__global__ void __launch_bounds__(kWalkThreads, 6)
 ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, const float2* __restrict__ stats,
                         const float2* __restrict__ rowstat, __nv_bfloat16* __restrict__ du,
                         float* __restrict__ dgamma, float* __restrict__ dconv_w, int rows_per_cta) {
+  constexpr int CH = kWalkCh;
   const int slabs = (a.N + rows_per_cta - 1) / rows_per_cta;
   const int b = blockIdx.x / slabs, t0 = (blockIdx.x - b * slabs) * rows_per_cta;
   const int t_end = min(a.N, t0 + rows_per_cta);
-  const int c0raw = (blockIdx.y * kWalkThreads + threadIdx.x) * 4;
-  const bool active = c0raw < a.Fp;                  // inactive lanes stay alive for the pair shuffles below
+  const int c0raw = (blockIdx.y * kWalkThreads + threadIdx.x) * CH;
+  const bool active = c0raw < a.Fp;                  // inactive lanes stay alive for the shuffles below
   const int c0 = active ? c0raw : 0;
-  const int chunk8 = c0 >> 3, sub = threadIdx.x & 1;  // dropout bits are defined per 8-channel chunk (one lane pair)
+  const int chunk8 = c0 >> 3, sub = threadIdx.x & 3;  // dropout bits are defined per 8-channel chunk (4 adjacent lanes)
   const long long row_base = static_cast<long long>(b) * a.N;
   const long ld = 2L * a.Fp;
-  float wa[4][3], wg[4][3], gm[4];
+  float wa[CH][3], wg[CH][3], gm[CH];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < CH; ++i) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) { wa[i][k] = a.conv_w[(c0 + i) * 3 + k]; wg[i][k] = a.conv_w[(a.Fp + c0 + i) * 3 + k]; }
     gm[i] = a.gamma[c0 + i];
@@ -268,48 +277,62 @@ ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, 
   const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
   const uint32_t thresh = static_cast<uint32_t>(a.drop_p * 65536.f);
   const unsigned long long seed = (a.drop_p > 0.f) ? *a.seed : 0ull;
-  float ua2[4], ua1[4], ug2[4], ug1[4];           // u rows t'-2, t'-1
+  float ua2[CH], ua1[CH], ug2[CH], ug1[CH];           // u rows t'-2, t'-1
   {
-    const bool ok2 = t0 - 2 >= 0, ok1 = t0 - 1 >= 0;
+    const bool ok2 = active && t0 - 2 >= 0, ok1 = active && t0 - 1 >= 0;
     const __nv_bfloat16* p2 = a.u + (row_base + t0 - 2) * ld + c0;
     const __nv_bfloat16* p1 = a.u + (row_base + t0 - 1) * ld + c0;
-    load4(p2, ok2, ua2); load4(p2 + a.Fp, ok2, ug2);
-    load4(p1, ok1, ua1); load4(p1 + a.Fp, ok1, ug1);
+    load2(p2, ok2, ua2); load2(p2 + a.Fp, ok2, ug2);
+    load2(p1, ok1, ua1); load2(p1 + a.Fp, ok1, ug1);
   }
-  float da2[4] = {0.f, 0.f, 0.f, 0.f}, da1[4] = {0.f, 0.f, 0.f, 0.f};   // dy rows t'-2, t'-1 (value half)
-  float dg2[4] = {0.f, 0.f, 0.f, 0.f}, dg1[4] = {0.f, 0.f, 0.f, 0.f};   // (gate half)
-  float dwa[4][3], dwg[4][3], dgam[4];
+  float da2[CH], da1[CH], dg2[CH], dg1[CH];   // dy rows t'-2, t'-1
+  float dwa[CH][3], dwg[CH][3], dgam[CH];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { dgam[i] = 0.f;
+  for (int i = 0; i < CH; ++i) { da2[i] = da1[i] = dg2[i] = dg1[i] = 0.f; dgam[i] = 0.f;
 #pragma unroll
     for (int k = 0; k < 3; ++k) { dwa[i][k] = 0.f; dwg[i][k] = 0.f; } }
 
+  // software pipeline: the (independent) loads of row t'+1 are issued before row t' is processed, so each
+  // iteration overlaps one L2/HBM round trip with the arithmetic of the previous row
+  struct RowIn { uint32_t ua, ug, d; float2 st, rs; };
+  auto fetch = [&](int tp) {
+    RowIn r;
+    r.ua = 0u; r.ug = 0u; r.d = 0u; r.st = make_float2(0.f, 0.f); r.rs = r.st;
+    if (active && tp < a.N) {
+      const long long row = row_base + tp;
+      r.ua = *reinterpret_cast<const uint32_t*>(a.u + row * ld + c0);
+      r.ug = *reinterpret_cast<const uint32_t*>(a.u + row * ld + a.Fp + c0);
+      r.d = *reinterpret_cast<const uint32_t*>(dhn + row * a.Fp + c0);
+      r.st = stats[row]; r.rs = rowstat[row];
+    }
+    return r;
+  };
+  RowIn cur = fetch(t0);
   for (int tp = t0; tp < t_end + 2; ++tp) {
     const bool valid = active && tp < a.N;
     const bool own = tp < t_end;                 // rows >= t_end are the next slab's: recomputed here only for the conv halo
     const long long row = row_base + tp;
-    float ua0[4], ug0[4], d[4];
-    load4(a.u + row * ld + c0, valid, ua0);
-    load4(a.u + row * ld + a.Fp + c0, valid, ug0);
-    load4(dhn + row * a.Fp + c0, valid, d);
-    float2 st = make_float2(0.f, 0.f), rs = make_float2(0.f, 0.f);
-    if (valid) { st = stats[row]; rs = rowstat[row]; }
+    const RowIn nxt = fetch(tp + 1 < t_end + 2 ? tp + 1 : a.N);
+    float ua0[CH], ug0[CH], d[CH];
+    { float2 x = unpack_bf16x2(cur.ua); ua0[0] = x.x; ua0[1] = x.y;
+      x = unpack_bf16x2(cur.ug); ug0[0] = x.x; ug0[1] = x.y;
+      x = unpack_bf16x2(cur.d); d[0] = x.x; d[1] = x.y; }
+    const float2 st = cur.st, rs = cur.rs;
     if (a.drop_p > 0.f) {
-      // one Philox call per 8-channel chunk: the even lane computes it, the odd lane borrows the upper 64 bits
+      // one Philox call per 8-channel chunk: lane 0 of each group of 4 computes it, the others borrow their 32 bits
       uint4 rnd = make_uint4(0, 0, 0, 0);
       if (sub == 0) rnd = philox4x32(static_cast<uint32_t>(row), static_cast<uint32_t>(row >> 32), static_cast<uint32_t>(chunk8), a.layer,
                                      static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
-      const uint32_t z = __shfl_sync(0xffffffffu, rnd.z, threadIdx.x & 30);
-      const uint32_t w = __shfl_sync(0xffffffffu, rnd.w, threadIdx.x & 30);
-      const uint32_t r01 = sub ? z : rnd.x, r23 = sub ? w : rnd.y;
-      d[0] = (r01 & 0xffffu) >= thresh ? d[0] * keep_scale : 0.f;
-      d[1] = (r01 >> 16) >= thresh ? d[1] * keep_scale : 0.f;
-      d[2] = (r23 & 0xffffu) >= thresh ? d[2] * keep_scale : 0.f;
-      d[3] = (r23 >> 16) >= thresh ? d[3] * keep_scale : 0.f;
+      const int src = threadIdx.x & 28;
+      const uint32_t x = __shfl_sync(0xffffffffu, rnd.x, src), y = __shfl_sync(0xffffffffu, rnd.y, src);
+      const uint32_t z = __shfl_sync(0xffffffffu, rnd.z, src), w = __shfl_sync(0xffffffffu, rnd.w, src);
+      const uint32_t bits = sub == 0 ? x : (sub == 1 ? y : (sub == 2 ? z : w));
+      d[0] = (bits & 0xffffu) >= thresh ? d[0] * keep_scale : 0.f;
+      d[1] = (bits >> 16) >= thresh ? d[1] * keep_scale : 0.f;
     }
-    float da0[4], dg0[4];
+    float da0[CH], dg0[CH];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < CH; ++i) {
       const float ya = wa[i][0] * ua2[i] + wa[i][1] * ua1[i] + wa[i][2] * ua0[i];
       const float yg = wg[i][0] * ug2[i] + wg[i][1] * ug1[i] + wg[i][2] * ug0[i];
       float phi, pdf;
@@ -327,24 +350,25 @@ ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, 
       }
     }
     if (active && tp - 2 >= t0) {  // du[t'-2] = w2 dy[t'-2] + w1 dy[t'-1] + w0 dy[t']
-      float oa[4], og[4];
+      float oa[CH], og[CH];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < CH; ++i) {
         oa[i] = wa[i][2] * da2[i] + wa[i][1] * da1[i] + wa[i][0] * da0[i];
         og[i] = wg[i][2] * dg2[i] + wg[i][1] * dg1[i] + wg[i][0] * dg0[i];
       }
-      store4(du + (row - 2) * ld + c0, oa);
-      store4(du + (row - 2) * ld + a.Fp + c0, og);
+      *reinterpret_cast<uint32_t*>(du + (row - 2) * ld + c0) = pack_bf16x2(oa[0], oa[1]);
+      *reinterpret_cast<uint32_t*>(du + (row - 2) * ld + a.Fp + c0) = pack_bf16x2(og[0], og[1]);
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < CH; ++i) {
       ua2[i] = ua1[i]; ua1[i] = ua0[i]; ug2[i] = ug1[i]; ug1[i] = ug0[i];
       da2[i] = da1[i]; da1[i] = da0[i]; dg2[i] = dg1[i]; dg1[i] = dg0[i];
     }
+    cur = nxt;
   }
   if (!active) return;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < CH; ++i) {
     atomicAdd(&dgamma[c0 + i], dgam[i]);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -387,7 +411,7 @@ int omlm_ffn_mid_bwd(const void* dhn, const void* hn, const void* u, const float
       reinterpret_cast<float2*>(rowstat_scratch), M, F, Fp, drop_p, seed, static_cast<uint32_t>(layer));
   OMLM_LAUNCH_CHECK();
   const int rows_per_cta = 32;
-  dim3 grid(B * ((N + rows_per_cta - 1) / rows_per_cta), (Fp / 4 + kWalkThreads - 1) / kWalkThreads);
+  dim3 grid(B * ((N + rows_per_cta - 1) / rows_per_cta), (Fp / kWalkCh + kWalkThreads - 1) / kWalkThreads);
   ffn_mid_bwd_walk_kernel<<<grid, kWalkThreads, 0, st>>>(a, reinterpret_cast<const __nv_bfloat16*>(dhn),
                                                          reinterpret_cast<const float2*>(stats),
                                                          reinterpret_cast<const float2*>(rowstat_scratch),

@@ -292,7 +292,7 @@ def run_b200(args):
             "e2e": {"value": tok / (ms_e2e * 1e-3), "unit": "tokens/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4},
             "gpu_launches": n_launch * args.steps, "gpu_launches_per_step": n_launch,
-            "launch_mode": "whole step replayed from one CUDA graph" if tr.use_cuda_graph else "eager launches",
+            "launch_mode": "step replayed from two CUDA graphs (fwd+bwd | clip+AdamW+pack), NCCL all-reduce eager between them" if tr.use_cuda_graph else "eager launches",
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all operand-major variants)", "achieved": ach,
                          "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": ach / peaks["sustained"], "traffic": None,
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']})",

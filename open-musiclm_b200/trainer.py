@@ -20,6 +20,7 @@ import torch
 import torch.distributed as dist
 
 from . import lib
+from .dist_utils import allreduce_sum_, grad_prescale, rank_seed, world_info
 from .model import TokenConditionedTransformer
 
 
@@ -39,9 +40,8 @@ class HotPathTrainer:
         self.betas, self.eps, self.pad_id = betas, eps, pad_id
         self.steps = 0
         self.pg = process_group
-        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
-        self.rank = dist.get_rank(process_group) if self.world > 1 else 0
-        eng.seed.fill_(seed * 1000003 + self.rank * 7919 + 1)     # per-rank random streams (dropout / forgetful mask)
+        self.world, self.rank = world_info(process_group)
+        eng.seed.fill_(rank_seed(seed, self.rank))     # per-rank random streams (dropout / forgetful mask)
         eng.adam_m = torch.zeros_like(eng.arena_p)
         eng.adam_v = torch.zeros_like(eng.arena_p)
         self.hyper_host = torch.zeros(9, dtype=torch.float32).pin_memory()
@@ -110,30 +110,38 @@ class HotPathTrainer:
         h[0] = self.lr * fac; h[1] = b1; h[2] = b2; h[3] = self.eps; h[4] = self.wd
         h[5] = 1 - b1 ** t; h[6] = 1 - b2 ** t
         h[7] = self.max_grad_norm if self.max_grad_norm is not None else 0.0
-        h[8] = 1.0 / self.world
+        h[8] = grad_prescale(self.pg)
         self.hyper.copy_(h, non_blocking=True)
 
-    def _step_body(self, micro_batches):
-        """Everything of one optimiser step that runs on the device (capturable in a CUDA graph)."""
+    def _fwd_bwd_body(self, micro_batches):
+        """Device work of one optimiser step up to the gradient arena (capturable in a CUDA graph)."""
         eng = self.eng
         eng.seed += 1
         for i, mb in enumerate(micro_batches):
             self._micro_batch(mb, True, i, True)
-        if self.world > 1:
-            dist.all_reduce(eng.arena_g, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def _update_body(self):
+        """Clip + AdamW + re-pack on the (already all-reduced) gradient arena (capturable in a CUDA graph)."""
+        eng = self.eng
         eng.sumsq.zero_()
         if self.max_grad_norm is not None:
-            lib.grad_sumsq(eng.arena_g, eng.sumsq, prescale=1.0 / self.world)
+            lib.grad_sumsq(eng.arena_g, eng.sumsq, prescale=grad_prescale(self.pg))
         lib.adamw_step(eng.arena_p, eng.arena_g, eng.adam_m, eng.adam_v, eng.n_decay, self.hyper, eng.sumsq)
         eng.arena_g.zero_()
         eng.refresh_packed(force=True)
         self.loss_out.copy_(self.loss_buf.sum() / self.grad_accum_every)
 
+    def _step_body(self, micro_batches):
+        self._fwd_bwd_body(micro_batches)
+        allreduce_sum_(self.eng.arena_g, self.pg)
+        self._update_body()
+
     def train_step(self, micro_batches: Sequence[Sequence[torch.Tensor]]):
         """One optimiser step over `grad_accum_every` micro-batches (each a tuple of token-id tensors in
         the stage's order, e.g. (clap, semantic, coarse); host or device).  Returns the mean loss as a device
-        scalar.  After two eager steps per input shape the whole step (~250 kernels) is replayed from a CUDA graph:
-        inputs are copied into static device buffers, hyper-parameters live in device memory."""
+        scalar.  After two eager steps per input shape the step is replayed from two CUDA graphs (forward+backward,
+        ~300 kernels; clip+AdamW+re-pack) with the NCCL gradient all-reduce launched eagerly between them; inputs are
+        copied into static device buffers, hyper-parameters live in device memory."""
         assert len(micro_batches) == self.grad_accum_every
         eng = self.eng
         self.transformer.train()
@@ -145,30 +153,37 @@ class HotPathTrainer:
         key = tuple(tuple(t.shape) for mb in micro_batches for t in mb)
         st = self._graphs.get(key)
         if st is None:
-            st = self._graphs[key] = dict(count=0, graph=None, static=[
+            st = self._graphs[key] = dict(count=0, graphs=None, static=[
                 [torch.empty(tuple(t.shape), dtype=torch.int64, device=eng.dev) for t in mb] for mb in micro_batches])
         for mb, smb in zip(micro_batches, st["static"]):
             for t, sbuf in zip(mb, smb):
                 sbuf.copy_(t, non_blocking=True)
-        if st["graph"] is not None:
-            st["graph"].replay()
+        if st["graphs"] is not None:
+            st["graphs"][0].replay()
+            allreduce_sum_(eng.arena_g, self.pg)
+            st["graphs"][1].replay()
         elif st["count"] < 2:
             self._step_body(st["static"])
             st["count"] += 1
         else:
             torch.cuda.synchronize()
             try:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._step_body(st["static"])
-                st["graph"] = g
-                g.replay()
+                ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(ga):
+                    self._fwd_bwd_body(st["static"])
+                with torch.cuda.graph(gb, pool=ga.pool()):
+                    self._update_body()
+                st["graphs"] = (ga, gb)
             except Exception as e:  # capture not possible in this environment: stay on the eager launch path (same kernels)
                 import warnings
                 warnings.warn(f"CUDA graph capture of the training step failed ({e}); continuing with eager launches")
                 self.use_cuda_graph = False
                 torch.cuda.synchronize()
                 self._step_body(st["static"])
+            else:
+                ga.replay()
+                allreduce_sum_(eng.arena_g, self.pg)
+                gb.replay()
         self.steps += 1
         return self.loss_out
 

@@ -30,7 +30,7 @@ int omlm_device_check(void);
  *   b_mn_major = 0: B is [N, ldb] with k contiguous;  1: B is [K, ldb] with n contiguous.
  *   out_f32: 0 -> bf16 out, 1 -> fp32 out.  addend (fp32, may alias out) gives residual add /
  *   beta=1 accumulation.  splits > 1: split-K with fp32 atomic accumulation into out.
- *   row_split/row_valid: output-row compaction for the padded GEGLU weight layout (0 = off).
+ *   row_split/row_valid: output-row compaction for padded GEGLU weight layouts (0 = off; >0 two halves; <0 interleaved-128).
  *   n_valid: number of live output columns (<= N; 0 = N).  block_n in {128, 256}.
  * Replaces nn.Linear / einsum: transformer.py:144,149,254,333; open_musiclm.py:173,181 and their
  * autograd backward GEMMs. */
@@ -119,12 +119,17 @@ int omlm_attn_bwd_tc(const void* qn, const void* kvn, const void* d_o, const voi
                      void* ds_scratch, float* dqn, float* dkvn, float* dtable, int B, int N, int heads,
                      float scale, void* stream);
 
-/* ---- ConvFeedForward middle (transformer.py:122-150): conv k=3 -> GEGLU -> LN(F) -> dropout ----
- * u bf16 [B*N, 2Fp] (value half | gate half), conv_w fp32 [2Fp,3], gamma fp32 [Fp] (packed/padded)
- * -> hn bf16 [B*N, Fp], stats fp32 [B*N, 2]. */
-int omlm_ffn_mid_fwd(const void* u, const float* conv_w, const float* gamma, void* hn, float* stats, int B,
-                     int N, int F, int Fp, float drop_p, const unsigned long long* seed, int layer,
-                     void* stream);
+/* ---- ConvFeedForward (transformer.py:122-150) ---------------------------------------------------
+ * Interleaved GEGLU layout: Fp = F rounded up to 128; u / W1 rows / conv taps are ordered in groups of 128 channels as
+ * [128 value | 128 gate]; h / hn / gamma / W2 columns are in natural channel order (zero padded to Fp).
+ * FFN up-projection GEMM (tcgen05) with the causal depthwise conv (k=3), GEGLU (exact erf) and the LayerNorm row
+ * statistics fused into its epilogue:  u bf16 [M, 2Fp], h bf16 [M, Fp], rowsum fp32 [M, 2] += (sum h, sum h^2)
+ * (rowsum must be zero on entry).  M = B * Nseq rows, sequences of Nseq consecutive rows. */
+int omlm_gemm_ffn_up(const void* xn, const void* w1_packed, const float* conv_w_packed, void* u_out, void* h_out,
+                     float* rowsum, int M, int Nseq, int K, int Fp, int max_ctas, void* stream);
+/* hn = dropout(LayerNorm_F(h)) from the fused statistics; stats fp32 [M, 2] = (mean, rstd) for the backward pass. */
+int omlm_ffn_norm_fwd(const void* h, const float* rowsum, const float* gamma, void* hn, float* stats, long M, int F,
+                      int Fp, float drop_p, const unsigned long long* seed, int layer, void* stream);
 /* dhn, hn (saved forward output) -> du bf16 [B*N, 2Fp]; dgamma [Fp] += ; dconv_w [2Fp,3] += ;
  * rowstat_scratch fp32 [B*N, 2]. */
 int omlm_ffn_mid_bwd(const void* dhn, const void* hn, const void* u, const float* stats, const float* conv_w,

@@ -62,6 +62,28 @@ __device__ __forceinline__ float bf16_round(float x) {
   return __bfloat162float(__float2bfloat16_rn(x));
 }
 
+// ---- GELU (exact erf) ------------------------------------------------------------------------
+// Exact-erf GELU pieces from ONE exponential: e = exp(-x^2/2) gives both the normal pdf and, through the
+// Abramowitz-Stegun 7.1.26 rational form (|error| <= 1.5e-7, below fp32 resolution of the products here),
+// erf(x/sqrt(2)).  cdf = Phi(x), pdf = phi(x);  gelu(x) = x*cdf, gelu'(x) = cdf + x*pdf.
+__device__ __forceinline__ void normal_cdf_pdf(float x, float& cdf, float& pdf) {
+  const float e = __expf(-0.5f * x * x);
+  const float ax = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float half_erfc = 0.5f * p * t * e;            // 0.5 * erfc(|x|/sqrt2)
+  cdf = x >= 0.f ? 1.f - half_erfc : half_erfc;
+  pdf = 0.3989422804014327f * e;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float c, p;
+  normal_cdf_pdf(x, c, p);
+  return x * c;
+}
+
 // Philox-4x32 counter RNG, 7 rounds (the shortest variant that passes BigCrush): dropout / forgetful-mask
 // randomness, replayable in the backward pass from (seed, layer, row, chunk).
 __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,

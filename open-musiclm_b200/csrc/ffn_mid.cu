@@ -1,41 +1,19 @@
-// The bandwidth-bound middle of ConvFeedForward between the two tensor-core GEMMs
-// (transformer.py:140-150):  causal depthwise conv k=3 (122-131) -> GEGLU with exact-erf GELU
-// (134-137) -> LayerNorm over the inner dim (147) -> dropout (148), fused in ONE pass over u.
+// The SIMT parts of ConvFeedForward that are NOT fused into a GEMM epilogue (transformer.py:140-150):
+//   forward : LayerNorm(F) + dropout on the h tile that the FFN-up GEMM epilogue produced (gemm_ffn_up.cu does the
+//             causal depthwise conv k=3 (122-131) and GEGLU with exact-erf GELU (134-137) under the MMA);
+//   backward: dropout/LN backward, GEGLU backward, transposed causal conv and the conv / gamma weight gradients.
 //
-// Layout: u is [M, 2*Fp] bf16 with the GEGLU value half in columns [0, Fp) and the gate half in
-// [Fp, 2*Fp) (Fp = inner dim F padded to a multiple of 64; padded weights are zero so padded
-// channels are exactly 0 everywhere).  A CTA owns a slab of kT consecutive time steps of ONE batch
-// element (the conv never crosses batch elements) and every thread owns 8 channels of both halves
-// (16-byte accesses); the two conv history rows are re-read (L2 hits) instead of staged.
+// Layout: u / du are [M, 2*Fp] bf16 in the INTERLEAVED GEGLU order: channels in groups of 128, each group stored as
+// [128 value columns | 128 gate columns] (Fp = F padded to a multiple of 128; padded weights are zero so padded
+// channels are exactly 0 everywhere).  h / hn / dhn are [M, Fp] in natural channel order.
 #include "common.cuh"
 #include "../../include/omlm_b200.h"
 
 namespace omlm {
 
-constexpr int kT = 8;   // time steps per slab (forward)
-constexpr int kTB = 4;  // time steps per slab (backward: three live values per element)
-constexpr int kMidMaxThreads = 384;
-
-// Exact-erf GELU pieces from ONE exponential: e = exp(-x^2/2) gives both the normal pdf and, through the
-// Abramowitz-Stegun 7.1.26 rational form (|error| <= 1.5e-7, below fp32 resolution of the products here),
-// erf(x/sqrt(2)).  cdf = Phi(x), pdf = phi(x);  gelu(x) = x*cdf, gelu'(x) = cdf + x*pdf.
-__device__ __forceinline__ void normal_cdf_pdf(float x, float& cdf, float& pdf) {
-  const float e = __expf(-0.5f * x * x);
-  const float ax = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float half_erfc = 0.5f * p * t * e;            // 0.5 * erfc(|x|/sqrt2)
-  cdf = x >= 0.f ? 1.f - half_erfc : half_erfc;
-  pdf = 0.3989422804014327f * e;
-}
-__device__ __forceinline__ float gelu_erf(float x) {
-  float c, p;
-  normal_cdf_pdf(x, c, p);
-  return x * c;
-}
+// Column of channel c's VALUE half in the interleaved u / W1 / conv layout: 128-channel groups stored as
+// [128 value columns | 128 gate columns] so that one 256-wide GEMM tile holds both halves of its channels.
+__device__ __forceinline__ int ileave(int c) { return ((c >> 7) << 8) + (c & 127); }
 
 __device__ __forceinline__ void load8(const __nv_bfloat16* p, bool ok, float (&f)[8]) {
   uint4 raw = make_uint4(0, 0, 0, 0);
@@ -51,25 +29,6 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
   o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
   o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
   *reinterpret_cast<uint4*>(p) = o;
-}
-
-// Sum T per-row partials over the whole block; result broadcast to every thread.
-template <int T>
-__device__ __forceinline__ void block_sum_rows(float (&v)[T], float* red /*[T][32]*/) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-#pragma unroll
-  for (int r = 0; r < T; ++r) v[r] = warp_sum(v[r]);
-  __syncthreads();
-  if (lane == 0) {
-#pragma unroll
-    for (int r = 0; r < T; ++r) red[r * 32 + warp] = v[r];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int r = 0; r < T; ++r) {
-    float s = lane < nw ? red[r * 32 + lane] : 0.f;
-    v[r] = warp_sum(s);
-  }
 }
 
 // keep flags for 8 channels of (row, chunk): 16 random bits per channel.
@@ -94,110 +53,47 @@ struct MidArgs {
 };
 
 // ------------------------------------------------------------------------------------------------
-// forward: hn = dropout(LN(gelu(conv(u)_gate) * conv(u)_value)),  stats = (mean, rstd) per row.
-// 4 channels per thread (of both halves): Fp/4 threads = 22 warps per CTA at Fp = 2752, one CTA per SM.
-constexpr int kFwdCh = 4;
-constexpr int kFwdMaxThreads = 704;
-
+// forward, second half: the FFN-up GEMM epilogue (gemm_ffn_up.cu) already produced h = gelu(conv(u)_gate) * conv(u)_value
+// as bf16 and the per-row sums (sum h, sum h^2) in fp32.  This kernel finishes LayerNorm(F) + dropout:
+//   hn = dropout((h - mean) * rstd * gamma),   stats[row] = (mean, rstd)  (kept for the backward pass).
+// One warp per row, 16-byte accesses; HBM-bound (2 * M * Fp * 2 bytes).
 __device__ __forceinline__ void load4(const __nv_bfloat16* p, bool ok, float (&f)[4]) {
   uint2 raw = make_uint2(0, 0);
   if (ok) raw = *reinterpret_cast<const uint2*>(p);
   const float2 a = unpack_bf16x2(raw.x), b = unpack_bf16x2(raw.y);
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
 }
-__device__ __forceinline__ void store4(__nv_bfloat16* p, const float (&f)[4]) {
-  uint2 o;
-  o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-  *reinterpret_cast<uint2*>(p) = o;
-}
 
-__global__ void __launch_bounds__(kFwdMaxThreads, 1)
-ffn_mid_fwd_kernel(const MidArgs a, __nv_bfloat16* __restrict__ hn, float2* __restrict__ stats) {
-  __shared__ float red[kT * 32];
-  const int slabs = (a.N + kT - 1) / kT;
-  const int b = blockIdx.x / slabs, t0 = (blockIdx.x - b * slabs) * kT;
-  const int c0 = threadIdx.x * kFwdCh;
-  const int chunk8 = c0 >> 3, sub = threadIdx.x & 1;
-  const bool live = c0 < a.Fp;
-  const long long row_base = static_cast<long long>(b) * a.N;
-  const long ld = 2L * a.Fp;
-  float wa[kFwdCh][3], wg[kFwdCh][3];
+__global__ void __launch_bounds__(256)
+ffn_norm_fwd_kernel(const __nv_bfloat16* __restrict__ h, const float2* __restrict__ rowsum,
+                    const float* __restrict__ gamma, __nv_bfloat16* __restrict__ hn, float2* __restrict__ stats,
+                    long M, int F, int Fp, float drop_p, const unsigned long long* __restrict__ seed_ptr, uint32_t layer) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * 8 + warp;
+  if (row >= M) return;
+  const float2 rsum = rowsum[row];
+  const float mean = rsum.x / F;
+  const float var = fmaxf(rsum.y / F - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + 1e-5f);
+  if (lane == 0) stats[row] = make_float2(mean, rstd);
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const uint32_t thresh = static_cast<uint32_t>(drop_p * 65536.f);
+  const unsigned long long seed = (drop_p > 0.f) ? *seed_ptr : 0ull;
+  for (int chunk = lane; chunk * 8 < Fp; chunk += 32) {
+    float v[8];
+    load8(h + row * Fp + chunk * 8, true, v);
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + chunk * 8);
+    const float4 g1 = *reinterpret_cast<const float4*>(gamma + chunk * 8 + 4);
+    const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    bool keep[8];
+    if (drop_p > 0.f) dropout_keep8(seed, layer, row, chunk, thresh, keep);
+    float o[8];
 #pragma unroll
-  for (int i = 0; i < kFwdCh; ++i)
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      wa[i][k] = live ? a.conv_w[(c0 + i) * 3 + k] : 0.f;
-      wg[i][k] = live ? a.conv_w[(a.Fp + c0 + i) * 3 + k] : 0.f;
+    for (int i = 0; i < 8; ++i) {
+      o[i] = (v[i] - mean) * rstd * gm[i];          // gamma is zero in the padding -> padded channels stay 0
+      if (drop_p > 0.f) o[i] = keep[i] ? o[i] * keep_scale : 0.f;
     }
-  float a2[kFwdCh], a1[kFwdCh], g2[kFwdCh], g1[kFwdCh];
-  {
-    const bool ok2 = live && t0 - 2 >= 0, ok1 = live && t0 - 1 >= 0;
-    const __nv_bfloat16* p2 = a.u + (row_base + t0 - 2) * ld + c0;
-    const __nv_bfloat16* p1 = a.u + (row_base + t0 - 1) * ld + c0;
-    load4(p2, ok2, a2); load4(p2 + a.Fp, ok2, g2);
-    load4(p1, ok1, a1); load4(p1 + a.Fp, ok1, g1);
-  }
-  float hv[kT][kFwdCh];
-  float s[kT];
-#pragma unroll
-  for (int r = 0; r < kT; ++r) {
-    const bool ok = live && (t0 + r) < a.N;
-    float ac[kFwdCh], gc[kFwdCh];
-    const __nv_bfloat16* p = a.u + (row_base + t0 + r) * ld + c0;
-    load4(p, ok, ac); load4(p + a.Fp, ok, gc);
-    s[r] = 0.f;
-#pragma unroll
-    for (int i = 0; i < kFwdCh; ++i) {
-      const float ya = wa[i][0] * a2[i] + wa[i][1] * a1[i] + wa[i][2] * ac[i];
-      const float yg = wg[i][0] * g2[i] + wg[i][1] * g1[i] + wg[i][2] * gc[i];
-      hv[r][i] = gelu_erf(yg) * ya;
-      s[r] += hv[r][i];
-      a2[i] = a1[i]; a1[i] = ac[i]; g2[i] = g1[i]; g1[i] = gc[i];
-    }
-  }
-  block_sum_rows(s, red);
-  float mean[kT], q[kT];
-#pragma unroll
-  for (int r = 0; r < kT; ++r) {
-    mean[r] = s[r] / a.F;
-    q[r] = 0.f;
-    if (live) {
-#pragma unroll
-      for (int i = 0; i < kFwdCh; ++i) { const float d = hv[r][i] - mean[r]; q[r] += d * d; }
-    }
-  }
-  block_sum_rows(q, red);
-  float gm[kFwdCh];
-#pragma unroll
-  for (int i = 0; i < kFwdCh; ++i) gm[i] = live ? a.gamma[c0 + i] : 0.f;
-  const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
-  const uint32_t thresh = static_cast<uint32_t>(a.drop_p * 65536.f);
-  const unsigned long long seed = (a.drop_p > 0.f) ? *a.seed : 0ull;
-#pragma unroll
-  for (int r = 0; r < kT; ++r) {
-    if (t0 + r >= a.N) break;            // uniform across the block
-    // padded channels are 0, each contributed (0-mean)^2 to q: remove them
-    const float var = (q[r] - (a.Fp - a.F) * mean[r] * mean[r]) / a.F;
-    const float rstd = rsqrtf(var + 1e-5f);
-    const long long row = row_base + t0 + r;
-    if (threadIdx.x == 0) stats[row] = make_float2(mean[r], rstd);
-    float o[kFwdCh];
-#pragma unroll
-    for (int i = 0; i < kFwdCh; ++i) o[i] = (hv[r][i] - mean[r]) * rstd * gm[i];
-    if (a.drop_p > 0.f) {
-      // one Philox call per 8-channel chunk: the even lane of each pair computes it, the odd lane borrows the upper half
-      uint4 rnd = make_uint4(0, 0, 0, 0);
-      if (sub == 0) rnd = philox4x32(static_cast<uint32_t>(row), static_cast<uint32_t>(row >> 32), static_cast<uint32_t>(chunk8), a.layer,
-                                     static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
-      const uint32_t z = __shfl_sync(0xffffffffu, rnd.z, threadIdx.x & 30);
-      const uint32_t w = __shfl_sync(0xffffffffu, rnd.w, threadIdx.x & 30);
-      const uint32_t r01 = sub ? z : rnd.x, r23 = sub ? w : rnd.y;
-      o[0] = (r01 & 0xffffu) >= thresh ? o[0] * keep_scale : 0.f;
-      o[1] = (r01 >> 16) >= thresh ? o[1] * keep_scale : 0.f;
-      o[2] = (r23 & 0xffffu) >= thresh ? o[2] * keep_scale : 0.f;
-      o[3] = (r23 >> 16) >= thresh ? o[3] * keep_scale : 0.f;
-    }
-    if (live) store4(hn + row * a.Fp + c0, o);
+    store8(hn + row * Fp + chunk * 8, o);
   }
 }
 
@@ -265,13 +161,14 @@ ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, 
   const bool active = c0raw < a.Fp;                  // inactive lanes stay alive for the shuffles below
   const int c0 = active ? c0raw : 0;
   const int chunk8 = c0 >> 3, sub = threadIdx.x & 3;  // dropout bits are defined per 8-channel chunk (4 adjacent lanes)
+  const int ca = ileave(c0);                          // column of this thread's value channels in u / du / conv_w (gate: +128)
   const long long row_base = static_cast<long long>(b) * a.N;
   const long ld = 2L * a.Fp;
   float wa[CH][3], wg[CH][3], gm[CH];
 #pragma unroll
   for (int i = 0; i < CH; ++i) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { wa[i][k] = a.conv_w[(c0 + i) * 3 + k]; wg[i][k] = a.conv_w[(a.Fp + c0 + i) * 3 + k]; }
+    for (int k = 0; k < 3; ++k) { wa[i][k] = a.conv_w[(ca + i) * 3 + k]; wg[i][k] = a.conv_w[(ca + 128 + i) * 3 + k]; }
     gm[i] = a.gamma[c0 + i];
   }
   const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
@@ -280,10 +177,10 @@ ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, 
   float ua2[CH], ua1[CH], ug2[CH], ug1[CH];           // u rows t'-2, t'-1
   {
     const bool ok2 = active && t0 - 2 >= 0, ok1 = active && t0 - 1 >= 0;
-    const __nv_bfloat16* p2 = a.u + (row_base + t0 - 2) * ld + c0;
-    const __nv_bfloat16* p1 = a.u + (row_base + t0 - 1) * ld + c0;
-    load2(p2, ok2, ua2); load2(p2 + a.Fp, ok2, ug2);
-    load2(p1, ok1, ua1); load2(p1 + a.Fp, ok1, ug1);
+    const __nv_bfloat16* p2 = a.u + (row_base + t0 - 2) * ld + ca;
+    const __nv_bfloat16* p1 = a.u + (row_base + t0 - 1) * ld + ca;
+    load2(p2, ok2, ua2); load2(p2 + 128, ok2, ug2);
+    load2(p1, ok1, ua1); load2(p1 + 128, ok1, ug1);
   }
   float da2[CH], da1[CH], dg2[CH], dg1[CH];   // dy rows t'-2, t'-1
   float dwa[CH][3], dwg[CH][3], dgam[CH];
@@ -300,8 +197,8 @@ ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, 
     r.ua = 0u; r.ug = 0u; r.d = 0u; r.st = make_float2(0.f, 0.f); r.rs = r.st;
     if (active && tp < a.N) {
       const long long row = row_base + tp;
-      r.ua = *reinterpret_cast<const uint32_t*>(a.u + row * ld + c0);
-      r.ug = *reinterpret_cast<const uint32_t*>(a.u + row * ld + a.Fp + c0);
+      r.ua = *reinterpret_cast<const uint32_t*>(a.u + row * ld + ca);
+      r.ug = *reinterpret_cast<const uint32_t*>(a.u + row * ld + ca + 128);
       r.d = *reinterpret_cast<const uint32_t*>(dhn + row * a.Fp + c0);
       r.st = stats[row]; r.rs = rowstat[row];
     }
@@ -356,8 +253,8 @@ ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, 
         oa[i] = wa[i][2] * da2[i] + wa[i][1] * da1[i] + wa[i][0] * da0[i];
         og[i] = wg[i][2] * dg2[i] + wg[i][1] * dg1[i] + wg[i][0] * dg0[i];
       }
-      *reinterpret_cast<uint32_t*>(du + (row - 2) * ld + c0) = pack_bf16x2(oa[0], oa[1]);
-      *reinterpret_cast<uint32_t*>(du + (row - 2) * ld + a.Fp + c0) = pack_bf16x2(og[0], og[1]);
+      *reinterpret_cast<uint32_t*>(du + (row - 2) * ld + ca) = pack_bf16x2(oa[0], oa[1]);
+      *reinterpret_cast<uint32_t*>(du + (row - 2) * ld + ca + 128) = pack_bf16x2(og[0], og[1]);
     }
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
@@ -372,28 +269,26 @@ ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, 
     atomicAdd(&dgamma[c0 + i], dgam[i]);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      atomicAdd(&dconv_w[(c0 + i) * 3 + k], dwa[i][k]);
-      atomicAdd(&dconv_w[(a.Fp + c0 + i) * 3 + k], dwg[i][k]);
+      atomicAdd(&dconv_w[(ca + i) * 3 + k], dwa[i][k]);
+      atomicAdd(&dconv_w[(ca + 128 + i) * 3 + k], dwg[i][k]);
     }
   }
 }
 
-static int mid_threads(int Fp) { return ((Fp / kFwdCh + 31) / 32) * 32; }
 
 }  // namespace omlm
 
 extern "C" {
 
-int omlm_ffn_mid_fwd(const void* u, const float* conv_w, const float* gamma, void* hn, float* stats, int B,
-                     int N, int F, int Fp, float drop_p, const unsigned long long* seed, int layer,
-                     void* stream) {
+int omlm_ffn_norm_fwd(const void* h, const float* rowsum, const float* gamma, void* hn, float* stats, long M, int F,
+                      int Fp, float drop_p, const unsigned long long* seed, int layer, void* stream) {
   using namespace omlm;
-  OMLM_CHECK_ARG(B > 0 && N > 0 && F > 0 && Fp >= F && Fp % 8 == 0 && Fp <= kFwdCh * kFwdMaxThreads, "ffn_mid_fwd: bad shape F=%d Fp=%d", F, Fp);
-  OMLM_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || seed != nullptr), "ffn_mid_fwd: bad dropout args");
-  MidArgs a{reinterpret_cast<const __nv_bfloat16*>(u), conv_w, gamma, N, F, Fp, drop_p, seed, static_cast<uint32_t>(layer)};
-  const int slabs = (N + kT - 1) / kT;
-  ffn_mid_fwd_kernel<<<B * slabs, mid_threads(Fp), 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      a, reinterpret_cast<__nv_bfloat16*>(hn), reinterpret_cast<float2*>(stats));
+  OMLM_CHECK_ARG(M > 0 && F > 0 && Fp >= F && Fp % 128 == 0, "ffn_norm_fwd: bad shape F=%d Fp=%d", F, Fp);
+  OMLM_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || seed != nullptr), "ffn_norm_fwd: bad dropout args");
+  ffn_norm_fwd_kernel<<<static_cast<int>((M + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(h), reinterpret_cast<const float2*>(rowsum), gamma,
+      reinterpret_cast<__nv_bfloat16*>(hn), reinterpret_cast<float2*>(stats), M, F, Fp, drop_p, seed,
+      static_cast<uint32_t>(layer));
   OMLM_LAUNCH_CHECK();
   return 0;
 }
@@ -402,7 +297,7 @@ int omlm_ffn_mid_bwd(const void* dhn, const void* hn, const void* u, const float
                      const float* gamma, float* rowstat_scratch, void* du, float* dgamma, float* dconv_w, int B, int N,
                      int F, int Fp, float drop_p, const unsigned long long* seed, int layer, void* stream) {
   using namespace omlm;
-  OMLM_CHECK_ARG(B > 0 && N > 0 && F > 0 && Fp >= F && Fp % 8 == 0 && Fp <= 8 * kMidMaxThreads, "ffn_mid_bwd: bad shape F=%d Fp=%d", F, Fp);
+  OMLM_CHECK_ARG(B > 0 && N > 0 && F > 0 && Fp >= F && Fp % 128 == 0, "ffn_mid_bwd: bad shape F=%d Fp=%d", F, Fp);
   auto st = reinterpret_cast<cudaStream_t>(stream);
   MidArgs a{reinterpret_cast<const __nv_bfloat16*>(u), conv_w, gamma, N, F, Fp, drop_p, seed, static_cast<uint32_t>(layer)};
   const long M = static_cast<long>(B) * N;

@@ -31,7 +31,7 @@ struct EpiParams {
   int out_f32;    // 0: bf16, 1: fp32
   int atomic;     // 1: red.add into fp32 out (split-K)
   int vec_ok;     // 16-byte vector stores allowed
-  int row_split;  // >0: rows are two halves of row_split, each with row_valid live rows
+  int row_split;  // >0: rows are two halves of row_split, each with row_valid live rows; <0: interleaved GEGLU groups of 128
   int row_valid;
   int n_valid;    // columns >= n_valid are dropped
 };
@@ -177,6 +177,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int half = row / ep.row_split, r = row - half * ep.row_split;
         row_ok = row_ok && r < ep.row_valid;
         row = half * ep.row_valid + r;
+      } else if (ep.row_split < 0) {   // interleaved GEGLU rows: [128 value | 128 gate] per group of 128 channels
+        const int w256 = row & 255, ch = ((row >> 8) << 7) + (w256 & 127);
+        row_ok = row_ok && ch < ep.row_valid;
+        row = (w256 >> 7) * ep.row_valid + ch;
       }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
       // residual / beta=1 addend: software-pipelined one 32-column chunk ahead so that its HBM latency overlaps

@@ -60,8 +60,10 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
 }
 
 // dst[r, c] = src[map(r), c] for c < cols_valid and live r, else 0.
-// map: if split_dst > 0: half = r / split_dst, rr = r % split_dst, live iff rr < split_src, src row = half*split_src + rr
-//      else live iff r < rows_valid.
+// map: split_dst > 0: half = r / split_dst, rr = r % split_dst, live iff rr < split_src, src row = half*split_src + rr
+//      split_dst < 0: interleaved GEGLU order, groups of 128 channels stored as [128 value rows | 128 gate rows]:
+//                     w = r % 256, c = (r / 256) * 128 + w % 128, src row = (w / 128) * split_src + c, live iff c < split_src
+//      split_dst = 0: live iff r < rows_valid.
 template <typename OutT>
 __global__ void pack_kernel(const float* __restrict__ src, long src_ld, int rows_valid, int cols_valid,
                             OutT* __restrict__ dst, long dst_ld, int rows_p, int cols_p, int split_dst, int split_src) {
@@ -74,6 +76,7 @@ __global__ void pack_kernel(const float* __restrict__ src, long src_ld, int rows
     const int r = static_cast<int>(i / c4n), c = static_cast<int>(i - static_cast<long>(r) * c4n) << 2;
     int sr = r; bool live = r < rows_valid;
     if (split_dst > 0) { const int half = r / split_dst, rr = r - half * split_dst; sr = half * split_src + rr; live = rr < split_src && sr < rows_valid; }
+    else if (split_dst < 0) { const int w = r & 255, c = ((r >> 8) << 7) + (w & 127); sr = (w >> 7) * split_src + c; live = c < split_src && sr < rows_valid; }
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (live) {
       if (vec_src && c + 3 < cols_valid) {
@@ -112,6 +115,7 @@ __global__ void unpack_add_kernel(const float* __restrict__ packed, long p_ld, i
     const int r = static_cast<int>(i / cols_p), c = static_cast<int>(i - static_cast<long>(r) * cols_p);
     int sr = r; bool live = r < rows_valid;
     if (split_dst > 0) { const int half = r / split_dst, rr = r - half * split_dst; live = rr < split_src; sr = half * split_src + rr; live = live && sr < rows_valid; }
+    else if (split_dst < 0) { const int w = r & 255, c = ((r >> 8) << 7) + (w & 127); sr = (w >> 7) * split_src + c; live = c < split_src && sr < rows_valid; }
     if (live && c < cols_valid) dst[sr * dst_ld + c] += packed[r * p_ld + c];
   }
 }

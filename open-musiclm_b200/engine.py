@@ -83,7 +83,7 @@ class Engine:
         self.d, self.L, self.h = module.dim, module.depth, module.heads
         self.HD = self.h * 64
         self.F = int(self.d * 2 * 4 / 3)
-        self.Fp = _round_up(self.F, 64)
+        self.Fp = _round_up(self.F, 128)           # interleaved GEGLU layout: groups of 128 channels
         self.Hr = self.d // 2                      # rel-pos MLP width
         self.C = [s.codebook_size + 1 for s in self.seqs]
         self.Cp = [_round_up(c, 64) for c in self.C]
@@ -172,9 +172,9 @@ class Engine:
             lib.pack(pv[p + "0.to_q.weight"], d, HD, d, pk["wq"], HD, d)
             lib.pack(pv[p + "0.to_kv.weight"], d, 128, d, pk["wkv"], 128, d)
             lib.pack(pv[p + "0.to_out.0.weight"], HD, d, HD, pk["wo"], d, HD)
-            lib.pack(pv[p + "2.1.weight"], d, 2 * F, d, pk["w1"], 2 * Fp, d, split_dst=Fp, split_src=F)
+            lib.pack(pv[p + "2.1.weight"], d, 2 * F, d, pk["w1"], 2 * Fp, d, split_dst=-1, split_src=F)
             lib.pack(pv[p + "2.6.weight"], F, d, F, pk["w2"], d, Fp)
-            lib.pack(pv[p + "2.2.ds_conv.weight"], 3, 2 * F, 3, pk["conv"], 2 * Fp, 3, split_dst=Fp, split_src=F)
+            lib.pack(pv[p + "2.2.ds_conv.weight"], 3, 2 * F, 3, pk["conv"], 2 * Fp, 3, split_dst=-1, split_src=F)
             lib.pack(pv[p + "2.4.gamma"], F, 1, F, pk["gin"], 1, Fp)
         for s, seq in enumerate(self.seqs):
             # [q, C, d] -> [q, Cp, d]: every head padded with zero rows
@@ -207,7 +207,7 @@ class Engine:
             o=[E(M, HD) for _ in range(nl)], lse=[E(M * h, dt=f32) for _ in range(nl)],
             xn2=[E(M, d) for _ in range(nl)], st_f=[E(M, 2, dt=f32) for _ in range(nl)],
             u=[E(M, 2 * Fp) for _ in range(nl)], hn=[E(M, Fp) for _ in range(nl)], st_i=[E(M, 2, dt=f32) for _ in range(nl)],
-            xf=E(max(pl.rows_total, 1), d), st_o=E(M, 2, dt=f32),
+            xf=E(max(pl.rows_total, 1), d), st_o=E(M, 2, dt=f32), h=E(M, Fp), rowsum=E(M, 2, dt=f32),
             logits=[E(max(pl.B * c, 1), self.Cp[s], dt=f32) for (s, qi, c, b0) in pl.groups],
             # rel-pos MLP
             rp_in=E(pl.N, 1, dt=f32), rp_z=[E(pl.N, self.Hr, dt=f32) for _ in range(3)],
@@ -284,8 +284,9 @@ class Engine:
             lib.attn_fwd_tc(ws["qn"][i], ws["kvn"][i], ws["table"], key_mask, ws["o"][i], ws["lse"][i], B, N, h)
             lib.gemm(ws["o"][i], pk["wo"], xm, addend=xa, block_n=self._bn_for(M, d, HD))
             lib.layernorm_fwd(xm, pv[p + "2.0.gamma"], ws["xn2"][i], None, ws["st_f"][i])
-            lib.gemm(ws["xn2"][i], pk["w1"], ws["u"][i], block_n=self._bn_for(M, 2 * Fp, d))
-            lib.ffn_mid_fwd(ws["u"][i], pk["conv"], pk["gin"], ws["hn"][i], ws["st_i"][i], B, N, F, Fp, drop_p, self.seed, l)
+            ws["rowsum"].zero_()
+            lib.gemm_ffn_up(ws["xn2"][i], pk["w1"], pk["conv"], ws["u"][i], ws["h"], ws["rowsum"], N, Fp)   # conv + GEGLU in the epilogue
+            lib.ffn_norm_fwd(ws["h"], ws["rowsum"], pk["gin"], ws["hn"][i], ws["st_i"][i], F, Fp, drop_p, self.seed, l)
             lib.gemm(ws["hn"][i], pk["w2"], xo, addend=xm, block_n=self._bn_for(M, d, Fp))
         x_last = x[2 * self.L] if train else x[0]
         lib.layernorm_fwd(x_last, pv["transformer.norm.gamma"], ws["xf"], None, ws["st_o"], pl.dest_row)
@@ -341,9 +342,9 @@ class Engine:
             lib.ffn_mid_bwd(ws["dhn"], ws["hn"][l], ws["u"][l], ws["st_i"][l], pk["conv"], pk["gin"], ws["rowstat"], ws["du"],
                             ws["dgin"], ws["dconv"], B, N, F, Fp, drop_p, self.seed, l)
             lib.unpack_add(ws["dgin"], 1, Fp, gv[p + "2.4.gamma"], F, 1, F)
-            lib.unpack_add(ws["dconv"], 2 * Fp, 3, gv[p + "2.2.ds_conv.weight"], 3, 2 * F, 3, split_dst=Fp, split_src=F)
+            lib.unpack_add(ws["dconv"], 2 * Fp, 3, gv[p + "2.2.ds_conv.weight"], 3, 2 * F, 3, split_dst=-1, split_src=F)
             lib.gemm(ws["du"], pk["w1"], ws["dxn"], b_mn=True, M=M, N=d, K=2 * Fp, block_n=self._bn_for(M, d, 2 * Fp))
-            self._wgrad(ws["du"], ws["xn2"][l], gv[p + "2.1.weight"], 2 * Fp, d, row_split=Fp, row_valid=F)
+            self._wgrad(ws["du"], ws["xn2"][l], gv[p + "2.1.weight"], 2 * Fp, d, row_split=-1, row_valid=F)
             lib.layernorm_bwd(ws["dxn"], xm, ws["st_f"][l], pv[p + "2.0.gamma"], dxb, gv[p + "2.0.gamma"], dres=dxa, dx_bf16=ws["dx_bf"])
             # ---- attention
             lib.gemm(ws["dx_bf"], pk["wo"], ws["d_o"], b_mn=True, M=M, N=HD, K=d, block_n=self._bn_for(M, HD, d))

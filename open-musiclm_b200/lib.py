@@ -206,9 +206,15 @@ def attn_bwd_tc(qn, kvn, d_o, o, lse2, table, key_mask, dsum_scratch, ds_scratch
          _p(dsum_scratch), _p(ds_scratch), _p(dqn), _p(dkvn), _p(dtable), _I(B), _I(N), _I(heads), _F(scale), _stream())
 
 
-def ffn_mid_fwd(u, conv_w, gamma, hn, stats, B, N, F, Fp, drop_p=0.0, seed=None, layer=0):
-    call("omlm_ffn_mid_fwd", _p(u), _p(conv_w), _p(gamma), _p(hn), _p(stats), _I(B), _I(N), _I(F), _I(Fp),
-         _F(drop_p), _p(seed), _I(layer), _stream())
+def gemm_ffn_up(xn, w1_packed, conv_w_packed, u_out, h_out, rowsum, Nseq, Fp, max_ctas=0):
+    M, K = xn.shape
+    call("omlm_gemm_ffn_up", _p(xn), _p(w1_packed), _p(conv_w_packed), _p(u_out), _p(h_out), _p(rowsum), _I(M), _I(Nseq),
+         _I(K), _I(Fp), _I(max_ctas), _stream())
+
+
+def ffn_norm_fwd(h, rowsum, gamma, hn, stats, F, Fp, drop_p=0.0, seed=None, layer=0):
+    call("omlm_ffn_norm_fwd", _p(h), _p(rowsum), _p(gamma), _p(hn), _p(stats), _L(h.shape[0]), _I(F), _I(Fp), _F(drop_p),
+         _p(seed), _I(layer), _stream())
 
 
 def ffn_mid_bwd(dhn, hn, u, stats, conv_w, gamma, rowstat, du, dgamma, dconv_w, B, N, F, Fp, drop_p=0.0, seed=None, layer=0):

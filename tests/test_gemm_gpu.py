@@ -55,6 +55,14 @@ def test_gemm_residual_and_splitk():
     full = dY.float().t() @ Xa.float()
     ref_dw = torch.cat([full[0:100, :300], full[128:228, :300]], 0)
     assert _rel(dW, ref_dw) < 1e-5
+    # interleaved GEGLU row order (groups of 128 channels: value rows | gate rows), F = 200 of Fp = 256
+    dY2 = torch.randn(M, 512, device="cuda").bfloat16()
+    dW2 = torch.zeros(400, 300, device="cuda")
+    lib.gemm(dY2, Xa, dW2, a_mn=True, b_mn=True, splits=2, row_split=-1, row_valid=200, n_valid=300)
+    full2 = dY2.float().t() @ Xa.float()            # packed rows: [0:128 value ch 0-127 | 128:256 gate ch 0-127 | 256:384 value ch 128-255 | ...]
+    val = torch.cat([full2[0:128], full2[256:256 + 72]], 0)[:, :300]
+    gate = torch.cat([full2[128:256], full2[384:384 + 72]], 0)[:, :300]
+    assert _rel(dW2, torch.cat([val, gate], 0)) < 1e-5
 
 
 def test_gemm_large_timing():

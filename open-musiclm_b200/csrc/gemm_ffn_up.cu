@@ -22,10 +22,9 @@ constexpr int kFuBM = 128, kFuBN = 256, kFuBK = 64, kFuStages = 3, kFuRowsOut = 
 constexpr int kFuA = kFuBM * kFuBK * 2, kFuB = kFuBN * kFuBK * 2, kFuStage = kFuA + kFuB;   // 16K + 32K
 constexpr int kFuUPitch = 528;                                   // bytes per row of the parked u tile
 constexpr int kFuOffU = kFuStages * kFuStage;                    // 147456
-constexpr int kFuOffW = kFuOffU + kFuBM * kFuUPitch;             // conv taps of this tile's 256 columns (float4 each)
-constexpr int kFuOffBar = kFuOffW + kFuBN * 16;
+constexpr int kFuOffBar = kFuOffU + kFuBM * kFuUPitch;
 constexpr int kFuSmem = kFuOffBar + 256 + 1024;
-constexpr int kFuThreads = 192;
+constexpr int kFuThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter / per SM sub-partition)
 
 __global__ void __launch_bounds__(kFuThreads, 1)
 gemm_ffn_up_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -39,7 +38,6 @@ gemm_ffn_up_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   uint8_t* usm = smem + kFuOffU;
-  float4* wsm = reinterpret_cast<float4*>(smem + kFuOffW);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (M + kFuRowsOut - 1) / kFuRowsOut;
@@ -51,7 +49,7 @@ gemm_ffn_up_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < kFuStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -101,30 +99,38 @@ gemm_ffn_up_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
   } else {
-    // -------------------------------------------------------------------------------------- epilogue warps (128 threads)
+    // -------------------------------------------------------------------------------------- epilogue warps (256 threads)
     const int quarter = warp & 3;
     const int t = quarter * 32 + lane;           // tile row owned by this thread (= TMEM lane)
-    const int et = threadIdx.x - 64;             // 0..127 within the epilogue group
+    const int et = threadIdx.x - 64;             // 0..255 within the epilogue group
+    const int half = et >> 7;                    // warps 2-5: first 64 channels of the tile, warps 6-9: last 64
     int acc = 0; uint32_t acc_phase = 0;
     bool first = true;
     for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
       const int n_blk = w % n_tiles, m_blk = w / n_tiles;
-      if (!first) asm volatile("bar.sync 2, 128;" ::: "memory");   // everyone is done reading the previous u tile / taps
+      if (!first) asm volatile("bar.sync 2, 256;" ::: "memory");   // everyone is done reading the previous u tile
       first = false;
-      // conv taps of this tile's 256 columns -> smem (3 scalar loads per column, two columns per thread)
+      // conv taps of this lane's 4 value + 4 gate channels (phase 2 mapping), fetched under the wait for the MMAs
+      float wv[4][3], wg[4][3];
+      {
+        const float4* wp = reinterpret_cast<const float4*>(conv_w + static_cast<long>(n_blk * kFuBN + lane * 4) * 3);
+        const float4* gp = reinterpret_cast<const float4*>(conv_w + static_cast<long>(n_blk * kFuBN + 128 + lane * 4) * 3);
+        const float4 a0 = __ldg(wp), a1 = __ldg(wp + 1), a2 = __ldg(wp + 2);
+        const float4 b0 = __ldg(gp), b1 = __ldg(gp + 1), b2 = __ldg(gp + 2);
+        const float fa[12] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
+        const float fb[12] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int col = et + i * 128;
-        const float* wp = conv_w + static_cast<long>(n_blk * kFuBN + col) * 3;
-        wsm[col] = make_float4(wp[0], wp[1], wp[2], 0.f);
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { wv[e][k] = fa[e * 3 + k]; wg[e][k] = fb[e * 3 + k]; }
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      // ---- phase 1: accumulators -> bf16 -> parked u tile
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kFuBN;
+      // ---- phase 1: accumulators -> bf16 -> parked u tile (this warp: its 32 rows x 128 of the 256 columns)
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kFuBN + half * 128;
       uint8_t* urow = usm + t * kFuUPitch;
 #pragma unroll 1
-      for (int c = 0; c < kFuBN / 32; ++c) {
+      for (int c = 0; c < 4; ++c) {
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
         tmem_ld_wait();
@@ -135,55 +141,82 @@ gemm_ffn_up_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           q.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
           q.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
           q.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
-          *reinterpret_cast<uint4*>(urow + c * 64 + j * 16) = q;
+          *reinterpret_cast<uint4*>(urow + half * 256 + c * 64 + j * 16) = q;
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);   // TMEM buffer free: the next tile's MMAs proceed under phase 2
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      asm volatile("bar.sync 2, 128;" ::: "memory");  // u tile + taps complete
-      // ---- phase 2: conv + GEGLU + row statistics on rows t >= 2 of the tile
-      const long grow = static_cast<long>(m_blk) * kFuRowsOut - 2 + t;
-      if (t >= 2 && grow < M) {
-        const int pos = static_cast<int>(grow % Nseq);
-        const float k1 = pos >= 1 ? 1.f : 0.f, k2 = pos >= 2 ? 1.f : 0.f;   // no history across sequence starts
-        const uint8_t* r0 = urow;
-        const uint8_t* r1 = urow - kFuUPitch;
-        const uint8_t* r2 = urow - 2 * kFuUPitch;
-        __nv_bfloat16* ug = u_out + grow * (2L * Fp) + n_blk * kFuBN;
-#pragma unroll 4
-        for (int j = 0; j < 32; ++j) reinterpret_cast<uint4*>(ug)[j] = reinterpret_cast<const uint4*>(r0)[j];
-        __nv_bfloat16* hg = h_out + grow * static_cast<long>(Fp) + n_blk * 128;
-        float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-        for (int j = 0; j < 16; ++j) {   // 8 channels per step
-          const uint4 a0 = reinterpret_cast<const uint4*>(r0)[j], a1 = reinterpret_cast<const uint4*>(r1)[j],
-                      a2 = reinterpret_cast<const uint4*>(r2)[j];
-          const uint4 g0 = reinterpret_cast<const uint4*>(r0 + 256)[j], g1 = reinterpret_cast<const uint4*>(r1 + 256)[j],
-                      g2 = reinterpret_cast<const uint4*>(r2 + 256)[j];
-          const uint32_t A0[4] = {a0.x, a0.y, a0.z, a0.w}, A1[4] = {a1.x, a1.y, a1.z, a1.w}, A2[4] = {a2.x, a2.y, a2.z, a2.w};
-          const uint32_t G0[4] = {g0.x, g0.y, g0.z, g0.w}, G1[4] = {g1.x, g1.y, g1.z, g1.w}, G2[4] = {g2.x, g2.y, g2.z, g2.w};
-          uint32_t hp[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 xa0 = unpack_bf16x2(A0[e]), xa1 = unpack_bf16x2(A1[e]), xa2 = unpack_bf16x2(A2[e]);
-            const float2 xg0 = unpack_bf16x2(G0[e]), xg1 = unpack_bf16x2(G1[e]), xg2 = unpack_bf16x2(G2[e]);
-            const float4 wa0 = wsm[j * 8 + 2 * e], wa1 = wsm[j * 8 + 2 * e + 1];
-            const float4 wg0 = wsm[128 + j * 8 + 2 * e], wg1 = wsm[128 + j * 8 + 2 * e + 1];
-            const float ya0 = wa0.x * (k2 * xa2.x) + wa0.y * (k1 * xa1.x) + wa0.z * xa0.x;
-            const float ya1 = wa1.x * (k2 * xa2.y) + wa1.y * (k1 * xa1.y) + wa1.z * xa0.y;
-            const float yg0 = wg0.x * (k2 * xg2.x) + wg0.y * (k1 * xg1.x) + wg0.z * xg0.x;
-            const float yg1 = wg1.x * (k2 * xg2.y) + wg1.y * (k1 * xg1.y) + wg1.z * xg0.y;
-            const float h0 = gelu_erf(yg0) * ya0, h1 = gelu_erf(yg1) * ya1;
-            s1 += h0 + h1;
-            s2 += h0 * h0 + h1 * h1;
-            hp[e] = pack_bf16x2(h0, h1);
-          }
-          reinterpret_cast<uint4*>(hg)[j] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+      asm volatile("bar.sync 2, 256;" ::: "memory");  // u tile complete
+      // ---- phase 2: conv + GEGLU + row statistics.  Warp ew owns tile rows 2+16 ew .. (16 rows), lanes span the 128
+      // channels (4 value + 4 gate columns each): every smem read and global store is contiguous across the warp, the
+      // two history rows slide through registers, and the row sums are reduced with one transposing butterfly.
+      {
+        const int ew = et >> 5;
+        const int t0 = 2 + ew * 16;
+        const long grow0 = static_cast<long>(m_blk) * kFuRowsOut - 2 + t0;
+        const int nrows = min(min(16, kFuBM - t0), static_cast<int>(min(static_cast<long>(16), M - grow0)));
+        int pos = static_cast<int>(grow0 % Nseq);
+        const uint8_t* rp = usm + t0 * kFuUPitch;
+        float xv1[4], xg1[4], xv2[4], xg2[4];
+        {
+          const uint2 a = *reinterpret_cast<const uint2*>(rp - kFuUPitch + lane * 8);
+          const uint2 g = *reinterpret_cast<const uint2*>(rp - kFuUPitch + 256 + lane * 8);
+          const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y);
+          xv1[0] = a0.x; xv1[1] = a0.y; xv1[2] = a1.x; xv1[3] = a1.y;
+          xg1[0] = g0.x; xg1[1] = g0.y; xg1[2] = g1.x; xg1[3] = g1.y;
         }
-        atomicAdd(rowsum + 2 * grow, s1);
-        atomicAdd(rowsum + 2 * grow + 1, s2);
+        {
+          const uint2 a = *reinterpret_cast<const uint2*>(rp - 2 * kFuUPitch + lane * 8);
+          const uint2 g = *reinterpret_cast<const uint2*>(rp - 2 * kFuUPitch + 256 + lane * 8);
+          const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y);
+          xv2[0] = a0.x; xv2[1] = a0.y; xv2[2] = a1.x; xv2[3] = a1.y;
+          xg2[0] = g0.x; xg2[1] = g0.y; xg2[2] = g1.x; xg2[3] = g1.y;
+        }
+        float st[32];
+        __nv_bfloat16* ug = u_out + grow0 * (2L * Fp) + n_blk * kFuBN + lane * 8;
+        __nv_bfloat16* hg = h_out + grow0 * static_cast<long>(Fp) + n_blk * 128 + lane * 4;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          float s1 = 0.f, s2 = 0.f;
+          if (r < nrows) {
+            const uint8_t* rr = rp + r * kFuUPitch;
+            *reinterpret_cast<uint4*>(ug + static_cast<long>(r) * (2L * Fp)) = *reinterpret_cast<const uint4*>(rr + lane * 16);
+            const uint2 a = *reinterpret_cast<const uint2*>(rr + lane * 8);
+            const uint2 g = *reinterpret_cast<const uint2*>(rr + 256 + lane * 8);
+            const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y);
+            const float xv0[4] = {a0.x, a0.y, a1.x, a1.y}, xg0[4] = {g0.x, g0.y, g1.x, g1.y};
+            const float k1 = pos >= 1 ? 1.f : 0.f, k2 = pos >= 2 ? 1.f : 0.f;   // no history across sequence starts
+            float h[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float yv = wv[e][2] * xv0[e] + k1 * (wv[e][1] * xv1[e]) + k2 * (wv[e][0] * xv2[e]);
+              const float yg = wg[e][2] * xg0[e] + k1 * (wg[e][1] * xg1[e]) + k2 * (wg[e][0] * xg2[e]);
+              h[e] = gelu_erf(yg) * yv;
+              s1 += h[e];
+              s2 += h[e] * h[e];
+              xv2[e] = xv1[e]; xv1[e] = xv0[e];
+              xg2[e] = xg1[e]; xg1[e] = xg0[e];
+            }
+            *reinterpret_cast<uint2*>(hg + static_cast<long>(r) * Fp) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+            if (++pos == Nseq) pos = 0;
+          }
+          st[2 * r] = s1;
+          st[2 * r + 1] = s2;
+        }
+        // transposing butterfly: lane l ends up with the warp-wide sum of st[l]
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          const bool hi = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < off; ++i) {
+            const float send = hi ? st[i] : st[i + off];
+            const float keep = hi ? st[i + off] : st[i];
+            st[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
+        }
+        if ((lane >> 1) < nrows) atomicAdd(rowsum + 2 * grow0 + lane, st[0]);
       }
     }
   }

@@ -127,14 +127,16 @@ int omlm_attn_bwd_tc(const void* qn, const void* kvn, const void* d_o, const voi
  * (rowsum must be zero on entry).  M = B * Nseq rows, sequences of Nseq consecutive rows. */
 int omlm_gemm_ffn_up(const void* xn, const void* w1_packed, const float* conv_w_packed, void* u_out, void* h_out,
                      float* rowsum, int M, int Nseq, int K, int Fp, int max_ctas, void* stream);
-/* hn = dropout(LayerNorm_F(h)) from the fused statistics; stats fp32 [M, 2] = (mean, rstd) for the backward pass. */
-int omlm_ffn_norm_fwd(const void* h, const float* rowsum, const float* gamma, void* hn, float* stats, long M, int F,
-                      int Fp, float drop_p, const unsigned long long* seed, int layer, void* stream);
-/* dhn, hn (saved forward output) -> du bf16 [B*N, 2Fp]; dgamma [Fp] += ; dconv_w [2Fp,3] += ;
- * rowstat_scratch fp32 [B*N, 2]. */
+/* hn = dropout(LayerNorm_F(h)) from the fused statistics; stats fp32 [M, 2] = (mean, rstd) for the backward pass.
+ * With drop_p > 0 the Philox keep mask is also written to keep_bits (uint8 [M, Fp/8], bit i of byte j = channel 8j+i)
+ * so the backward pass reads 1 bit per element instead of regenerating the random stream. */
+int omlm_ffn_norm_fwd(const void* h, const float* rowsum, const float* gamma, void* hn, float* stats, void* keep_bits,
+                      long M, int F, int Fp, float drop_p, const unsigned long long* seed, int layer, void* stream);
+/* dhn, hn (saved forward output), keep_bits (from omlm_ffn_norm_fwd; may be NULL when drop_p == 0) ->
+ * du bf16 [B*N, 2Fp]; dgamma [Fp] += ; dconv_w [2Fp,3] += ; rowstat_scratch fp32 [B*N, 2]. */
 int omlm_ffn_mid_bwd(const void* dhn, const void* hn, const void* u, const float* stats, const float* conv_w,
-                     const float* gamma, float* rowstat_scratch, void* du, float* dgamma, float* dconv_w, int B, int N,
-                     int F, int Fp, float drop_p, const unsigned long long* seed, int layer, void* stream);
+                     const float* gamma, const void* keep_bits, float* rowstat_scratch, void* du, float* dgamma,
+                     float* dconv_w, int B, int N, int F, int Fp, float drop_p, void* stream);
 
 /* ---- cross entropy (open_musiclm.py:401) --------------------------------------------------------
  * loss_acc[0] += sum of row losses, loss_acc[1] += rows counted; dlogits bf16 [rows, ldd] =

@@ -7,6 +7,7 @@
 // [128 value columns | 128 gate columns] (Fp = F padded to a multiple of 128; padded weights are zero so padded
 // channels are exactly 0 everywhere).  h / hn / dhn are [M, Fp] in natural channel order.
 #include "common.cuh"
+#include "ptx.cuh"
 #include "../../include/omlm_b200.h"
 
 namespace omlm {
@@ -48,8 +49,7 @@ struct MidArgs {
   const float* gamma;         // [Fp] packed (zeros in the padding)
   int N, F, Fp;
   float drop_p;               // 0 -> no dropout
-  const unsigned long long* seed;
-  uint32_t layer;
+  const uint8_t* keep_bits;   // [M, Fp/8] dropout keep mask written by ffn_norm_fwd (bit i of byte j: channel 8 j + i)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -67,7 +67,8 @@ __device__ __forceinline__ void load4(const __nv_bfloat16* p, bool ok, float (&f
 __global__ void __launch_bounds__(256)
 ffn_norm_fwd_kernel(const __nv_bfloat16* __restrict__ h, const float2* __restrict__ rowsum,
                     const float* __restrict__ gamma, __nv_bfloat16* __restrict__ hn, float2* __restrict__ stats,
-                    long M, int F, int Fp, float drop_p, const unsigned long long* __restrict__ seed_ptr, uint32_t layer) {
+                    uint8_t* __restrict__ keep_bits, long M, int F, int Fp, float drop_p,
+                    const unsigned long long* __restrict__ seed_ptr, uint32_t layer) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long row = static_cast<long>(blockIdx.x) * 8 + warp;
   if (row >= M) return;
@@ -94,6 +95,12 @@ ffn_norm_fwd_kernel(const __nv_bfloat16* __restrict__ h, const float2* __restric
       if (drop_p > 0.f) o[i] = keep[i] ? o[i] * keep_scale : 0.f;
     }
     store8(hn + row * Fp + chunk * 8, o);
+    if (drop_p > 0.f) {   // the backward pass reads the mask back (1 bit per element) instead of replaying Philox
+      uint32_t bits = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) bits |= (keep[i] ? 1u : 0u) << i;
+      keep_bits[row * (Fp >> 3) + chunk] = static_cast<uint8_t>(bits);
+    }
   }
 }
 
@@ -111,26 +118,23 @@ ffn_norm_fwd_kernel(const __nv_bfloat16* __restrict__ h, const float2* __restric
 __global__ void __launch_bounds__(256)
 ffn_mid_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dhn, const __nv_bfloat16* __restrict__ hn,
                          const float* __restrict__ gamma, float2* __restrict__ rowstat, long M, int F, int Fp,
-                         float drop_p, const unsigned long long* __restrict__ seed_ptr, uint32_t layer) {
+                         float drop_p, const uint8_t* __restrict__ keep_bits) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long row = static_cast<long>(blockIdx.x) * 8 + warp;
   if (row >= M) return;
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  const uint32_t thresh = static_cast<uint32_t>(drop_p * 65536.f);
-  const unsigned long long seed = (drop_p > 0.f) ? *seed_ptr : 0ull;
   float s1 = 0.f, s2 = 0.f;
   for (int chunk = lane; chunk * 8 < Fp; chunk += 32) {
     float d[8], hv[8];
     load8(dhn + row * Fp + chunk * 8, true, d);
     load8(hn + row * Fp + chunk * 8, true, hv);
-    bool keep[8];
-    if (drop_p > 0.f) dropout_keep8(seed, layer, row, chunk, thresh, keep);
+    const uint32_t kb = drop_p > 0.f ? keep_bits[row * (Fp >> 3) + chunk] : 0xffu;
     const float4 g0 = *reinterpret_cast<const float4*>(gamma + chunk * 8);
     const float4 g1 = *reinterpret_cast<const float4*>(gamma + chunk * 8 + 4);
     const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float g = (drop_p > 0.f && !keep[i]) ? 0.f : d[i] * keep_scale;
+      const float g = ((kb >> i) & 1u) ? d[i] * keep_scale : 0.f;
       s1 += gm[i] * g;
       s2 += d[i] * hv[i];
     }
@@ -139,178 +143,238 @@ ffn_mid_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dhn, const __nv_bfloa
   if (lane == 0) rowstat[row] = make_float2(s1 / F, s2 / F);
 }
 
-constexpr int kWalkThreads = 128;
-constexpr int kWalkCh = 2;   // channels (of each GEGLU half) per thread: small footprint -> many resident warps
+// Tile geometry of the walk: a CTA owns 128 time steps x one 128-channel group (= 256 contiguous u columns in the
+// interleaved layout).  All operands of the tile (u with a 2-row history + 2-row look-ahead, dhn, the per-row LN
+// constants and the keep bits) are brought to shared memory with 16-byte cp.async in one burst -- every byte of the
+// tile is in flight at once, which is what the HBM latency needs -- and two CTAs per SM overlap one tile's load with
+// the other's arithmetic.  Each of the 8 warps then walks a 16-row slab with lanes across channels (4 value + 4 gate
+// per lane): shared-memory reads and global stores are contiguous across the warp, the conv windows slide through
+// registers.
+constexpr int kTileRows = 128, kTileWarps = 8, kTileSlab = 16, kTileThreads = kTileWarps * 32;
+constexpr int kTuRows = kTileRows + 4, kTdRows = kTileRows + 2;
+constexpr int kTOffU = 0;                               // [132][512 B]  u rows tb-2 .. tb+129
+constexpr int kTOffD = kTOffU + kTuRows * 512;          // [130][256 B]  dhn rows tb .. tb+129
+constexpr int kTOffS = kTOffD + kTdRows * 256;          // [130] float4 (mean, rstd, m1, m2)
+constexpr int kTOffK = kTOffS + kTdRows * 16;           // [130][16 B] keep bits of the group's 128 channels
+constexpr int kTOffAcc = kTOffK + kTdRows * 16;         // [7][128] fp32: dgamma, dconv value taps, dconv gate taps
+constexpr int kTileSmem = kTOffAcc + 7 * 128 * 4;
 
-__device__ __forceinline__ void load2(const __nv_bfloat16* p, bool ok, float (&f)[2]) {
-  uint32_t raw = 0;
-  if (ok) raw = *reinterpret_cast<const uint32_t*>(p);
-  const float2 a = unpack_bf16x2(raw);
-  f[0] = a.x; f[1] = a.y;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool ok) {
+  const int n = ok ? 16 : 0;   // src-size 0 -> the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool ok) {
+  const int n = ok ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(n) : "memory");
 }
 
-__global__ void __launch_bounds__(kWalkThreads, 6)
+__global__ void __launch_bounds__(kTileThreads, 2)
 ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, const float2* __restrict__ stats,
                         const float2* __restrict__ rowstat, __nv_bfloat16* __restrict__ du,
-                        float* __restrict__ dgamma, float* __restrict__ dconv_w, int rows_per_cta) {
-  constexpr int CH = kWalkCh;
-  const int slabs = (a.N + rows_per_cta - 1) / rows_per_cta;
-  const int b = blockIdx.x / slabs, t0 = (blockIdx.x - b * slabs) * rows_per_cta;
-  const int t_end = min(a.N, t0 + rows_per_cta);
-  const int c0raw = (blockIdx.y * kWalkThreads + threadIdx.x) * CH;
-  const bool active = c0raw < a.Fp;                  // inactive lanes stay alive for the shuffles below
-  const int c0 = active ? c0raw : 0;
-  const int chunk8 = c0 >> 3, sub = threadIdx.x & 3;  // dropout bits are defined per 8-channel chunk (4 adjacent lanes)
-  const int ca = ileave(c0);                          // column of this thread's value channels in u / du / conv_w (gate: +128)
+                        float* __restrict__ dgamma, float* __restrict__ dconv_w) {
+  extern __shared__ __align__(16) uint8_t tsm[];
+  uint8_t* su = tsm + kTOffU;
+  uint8_t* sd = tsm + kTOffD;
+  float4* sst = reinterpret_cast<float4*>(tsm + kTOffS);
+  uint8_t* skb = tsm + kTOffK;
+  float* sacc = reinterpret_cast<float*>(tsm + kTOffAcc);
+
+  const int blocks_per_seq = (a.N + kTileRows - 1) / kTileRows;
+  const int b = blockIdx.x / blocks_per_seq, tb = (blockIdx.x - b * blocks_per_seq) * kTileRows;
+  const int g = blockIdx.y;                            // 128-channel group
   const long long row_base = static_cast<long long>(b) * a.N;
   const long ld = 2L * a.Fp;
-  float wa[CH][3], wg[CH][3], gm[CH];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- one burst of async copies for the whole tile
+  for (int idx = tid; idx < kTuRows * 32; idx += kTileThreads) {
+    const int j = idx >> 5, c = idx & 31, t = tb - 2 + j;
+    const bool ok = t >= 0 && t < a.N;
+    cp_async16(su + j * 512 + c * 16, a.u + (row_base + (ok ? t : 0)) * ld + g * 256 + c * 8, ok);
+  }
+  for (int idx = tid; idx < kTdRows * 16; idx += kTileThreads) {
+    const int j = idx >> 4, c = idx & 15, t = tb + j;
+    const bool ok = t < a.N;
+    cp_async16(sd + j * 256 + c * 16, dhn + (row_base + (ok ? t : 0)) * a.Fp + g * 128 + c * 8, ok);
+  }
+  if (tid < kTdRows) {
+    const int t = tb + tid;
+    const bool ok = t < a.N;
+    const long long row = row_base + (ok ? t : 0);
+    cp_async8(reinterpret_cast<uint8_t*>(sst + tid), stats + row, ok);
+    cp_async8(reinterpret_cast<uint8_t*>(sst + tid) + 8, rowstat + row, ok);
+    if (a.drop_p > 0.f) cp_async16(skb + tid * 16, a.keep_bits + row * (a.Fp >> 3) + g * 16, ok);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int i = tid; i < 7 * 128; i += kTileThreads) sacc[i] = 0.f;
+
+  // ---- per-lane constants: 4 value + 4 gate channels
+  const int c0 = g * 128 + lane * 4;                   // natural channel index of this lane's first channel
+  float wa[4][3], wg[4][3], gm[4];
+  {
+    const float4* wp = reinterpret_cast<const float4*>(a.conv_w + static_cast<long>(g * 256 + lane * 4) * 3);
+    const float4* gp = reinterpret_cast<const float4*>(a.conv_w + static_cast<long>(g * 256 + 128 + lane * 4) * 3);
+    const float4 a0 = __ldg(wp), a1 = __ldg(wp + 1), a2 = __ldg(wp + 2);
+    const float4 b0 = __ldg(gp), b1 = __ldg(gp + 1), b2 = __ldg(gp + 2);
+    const float fa[12] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
+    const float fb[12] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
 #pragma unroll
-  for (int i = 0; i < CH; ++i) {
+    for (int e = 0; e < 4; ++e)
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { wa[i][k] = a.conv_w[(ca + i) * 3 + k]; wg[i][k] = a.conv_w[(ca + 128 + i) * 3 + k]; }
-    gm[i] = a.gamma[c0 + i];
+      for (int k = 0; k < 3; ++k) { wa[e][k] = fa[e * 3 + k]; wg[e][k] = fb[e * 3 + k]; }
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(a.gamma + c0));
+    gm[0] = gg.x; gm[1] = gg.y; gm[2] = gg.z; gm[3] = gg.w;      // zero in the padding -> padded channels give dh = 0
   }
   const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
-  const uint32_t thresh = static_cast<uint32_t>(a.drop_p * 65536.f);
-  const unsigned long long seed = (a.drop_p > 0.f) ? *a.seed : 0ull;
-  float ua2[CH], ua1[CH], ug2[CH], ug1[CH];           // u rows t'-2, t'-1
-  {
-    const bool ok2 = active && t0 - 2 >= 0, ok1 = active && t0 - 1 >= 0;
-    const __nv_bfloat16* p2 = a.u + (row_base + t0 - 2) * ld + ca;
-    const __nv_bfloat16* p1 = a.u + (row_base + t0 - 1) * ld + ca;
-    load2(p2, ok2, ua2); load2(p2 + 128, ok2, ug2);
-    load2(p1, ok1, ua1); load2(p1 + 128, ok1, ug1);
-  }
-  float da2[CH], da1[CH], dg2[CH], dg1[CH];   // dy rows t'-2, t'-1
-  float dwa[CH][3], dwg[CH][3], dgam[CH];
-#pragma unroll
-  for (int i = 0; i < CH; ++i) { da2[i] = da1[i] = dg2[i] = dg1[i] = 0.f; dgam[i] = 0.f;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { dwa[i][k] = 0.f; dwg[i][k] = 0.f; } }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
 
-  // software pipeline: the (independent) loads of row t'+1 are issued before row t' is processed, so each
-  // iteration overlaps one L2/HBM round trip with the arithmetic of the previous row
-  struct RowIn { uint32_t ua, ug, d; float2 st, rs; };
-  auto fetch = [&](int tp) {
-    RowIn r;
-    r.ua = 0u; r.ug = 0u; r.d = 0u; r.st = make_float2(0.f, 0.f); r.rs = r.st;
-    if (active && tp < a.N) {
-      const long long row = row_base + tp;
-      r.ua = *reinterpret_cast<const uint32_t*>(a.u + row * ld + ca);
-      r.ug = *reinterpret_cast<const uint32_t*>(a.u + row * ld + ca + 128);
-      r.d = *reinterpret_cast<const uint32_t*>(dhn + row * a.Fp + c0);
-      r.st = stats[row]; r.rs = rowstat[row];
-    }
-    return r;
-  };
-  RowIn cur = fetch(t0);
-  for (int tp = t0; tp < t_end + 2; ++tp) {
-    const bool valid = active && tp < a.N;
-    const bool own = tp < t_end;                 // rows >= t_end are the next slab's: recomputed here only for the conv halo
-    const long long row = row_base + tp;
-    const RowIn nxt = fetch(tp + 1 < t_end + 2 ? tp + 1 : a.N);
-    float ua0[CH], ug0[CH], d[CH];
-    { float2 x = unpack_bf16x2(cur.ua); ua0[0] = x.x; ua0[1] = x.y;
-      x = unpack_bf16x2(cur.ug); ug0[0] = x.x; ug0[1] = x.y;
-      x = unpack_bf16x2(cur.d); d[0] = x.x; d[1] = x.y; }
-    const float2 st = cur.st, rs = cur.rs;
-    if (a.drop_p > 0.f) {
-      // one Philox call per 8-channel chunk: lane 0 of each group of 4 computes it, the others borrow their 32 bits
-      uint4 rnd = make_uint4(0, 0, 0, 0);
-      if (sub == 0) rnd = philox4x32(static_cast<uint32_t>(row), static_cast<uint32_t>(row >> 32), static_cast<uint32_t>(chunk8), a.layer,
-                                     static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
-      const int src = threadIdx.x & 28;
-      const uint32_t x = __shfl_sync(0xffffffffu, rnd.x, src), y = __shfl_sync(0xffffffffu, rnd.y, src);
-      const uint32_t z = __shfl_sync(0xffffffffu, rnd.z, src), w = __shfl_sync(0xffffffffu, rnd.w, src);
-      const uint32_t bits = sub == 0 ? x : (sub == 1 ? y : (sub == 2 ? z : w));
-      d[0] = (bits & 0xffffu) >= thresh ? d[0] * keep_scale : 0.f;
-      d[1] = (bits >> 16) >= thresh ? d[1] * keep_scale : 0.f;
-    }
-    float da0[CH], dg0[CH];
-#pragma unroll
-    for (int i = 0; i < CH; ++i) {
-      const float ya = wa[i][0] * ua2[i] + wa[i][1] * ua1[i] + wa[i][2] * ua0[i];
-      const float yg = wg[i][0] * ug2[i] + wg[i][1] * ug1[i] + wg[i][2] * ug0[i];
-      float phi, pdf;
-      normal_cdf_pdf(yg, phi, pdf);
-      const float ge = yg * phi;
-      const float hhat = (ge * ya - st.x) * st.y;
-      const bool real = valid && (c0 + i < a.F);
-      const float dh = real ? st.y * (gm[i] * d[i] - rs.x - hhat * rs.y) : 0.f;
-      da0[i] = dh * ge;
-      dg0[i] = dh * ya * fmaf(yg, pdf, phi);
-      if (own && real) {
-        dgam[i] += d[i] * hhat;
-        dwa[i][0] += da0[i] * ua2[i]; dwa[i][1] += da0[i] * ua1[i]; dwa[i][2] += da0[i] * ua0[i];
-        dwg[i][0] += dg0[i] * ug2[i]; dwg[i][1] += dg0[i] * ug1[i]; dwg[i][2] += dg0[i] * ug0[i];
-      }
-    }
-    if (active && tp - 2 >= t0) {  // du[t'-2] = w2 dy[t'-2] + w1 dy[t'-1] + w0 dy[t']
-      float oa[CH], og[CH];
-#pragma unroll
-      for (int i = 0; i < CH; ++i) {
-        oa[i] = wa[i][2] * da2[i] + wa[i][1] * da1[i] + wa[i][0] * da0[i];
-        og[i] = wg[i][2] * dg2[i] + wg[i][1] * dg1[i] + wg[i][0] * dg0[i];
-      }
-      *reinterpret_cast<uint32_t*>(du + (row - 2) * ld + ca) = pack_bf16x2(oa[0], oa[1]);
-      *reinterpret_cast<uint32_t*>(du + (row - 2) * ld + ca + 128) = pack_bf16x2(og[0], og[1]);
-    }
-#pragma unroll
-    for (int i = 0; i < CH; ++i) {
-      ua2[i] = ua1[i]; ua1[i] = ua0[i]; ug2[i] = ug1[i]; ug1[i] = ug0[i];
-      da2[i] = da1[i]; da1[i] = da0[i]; dg2[i] = dg1[i]; dg1[i] = dg0[i];
-    }
-    cur = nxt;
+  // ---- walk this warp's slab: rows tb + 16 warp .. +15, plus two look-ahead rows for the transposed conv
+  const int ts = warp * kTileSlab;
+  float ua2[4], ua1[4], ug2[4], ug1[4];
+  {
+    const uint2 p2 = *reinterpret_cast<const uint2*>(su + ts * 512 + lane * 8);
+    const uint2 q2 = *reinterpret_cast<const uint2*>(su + ts * 512 + 256 + lane * 8);
+    const uint2 p1 = *reinterpret_cast<const uint2*>(su + (ts + 1) * 512 + lane * 8);
+    const uint2 q1 = *reinterpret_cast<const uint2*>(su + (ts + 1) * 512 + 256 + lane * 8);
+    float2 x;
+    x = unpack_bf16x2(p2.x); ua2[0] = x.x; ua2[1] = x.y; x = unpack_bf16x2(p2.y); ua2[2] = x.x; ua2[3] = x.y;
+    x = unpack_bf16x2(q2.x); ug2[0] = x.x; ug2[1] = x.y; x = unpack_bf16x2(q2.y); ug2[2] = x.x; ug2[3] = x.y;
+    x = unpack_bf16x2(p1.x); ua1[0] = x.x; ua1[1] = x.y; x = unpack_bf16x2(p1.y); ua1[2] = x.x; ua1[3] = x.y;
+    x = unpack_bf16x2(q1.x); ug1[0] = x.x; ug1[1] = x.y; x = unpack_bf16x2(q1.y); ug1[2] = x.x; ug1[3] = x.y;
   }
-  if (!active) return;
+  float da2[4], da1[4], dg2[4], dg1[4], dwa[4][3], dwg[4][3], dgam[4];
 #pragma unroll
-  for (int i = 0; i < CH; ++i) {
-    atomicAdd(&dgamma[c0 + i], dgam[i]);
+  for (int e = 0; e < 4; ++e) {
+    da2[e] = da1[e] = dg2[e] = dg1[e] = 0.f; dgam[e] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { dwa[e][k] = 0.f; dwg[e][k] = 0.f; }
+  }
+  const int kshift = (lane & 1) * 4;
+  __nv_bfloat16* du_lane = du + (row_base + tb + ts) * ld + g * 256 + lane * 4;
+#pragma unroll 3
+  for (int i = 0; i < kTileSlab + 2; ++i) {
+    const int tl = ts + i;                              // row tb + tl
+    const bool valid = tb + tl < a.N;
+    const bool own = i < kTileSlab;                      // later rows are recomputed only for the conv look-ahead
+    float ua0[4], ug0[4], da0[4], dg0[4];
+    {
+      const uint2 p = *reinterpret_cast<const uint2*>(su + (tl + 2) * 512 + lane * 8);
+      const uint2 q = *reinterpret_cast<const uint2*>(su + (tl + 2) * 512 + 256 + lane * 8);
+      float2 x;
+      x = unpack_bf16x2(p.x); ua0[0] = x.x; ua0[1] = x.y; x = unpack_bf16x2(p.y); ua0[2] = x.x; ua0[3] = x.y;
+      x = unpack_bf16x2(q.x); ug0[0] = x.x; ug0[1] = x.y; x = unpack_bf16x2(q.y); ug0[2] = x.x; ug0[3] = x.y;
+    }
+    if (valid) {
+      const uint2 dr = *reinterpret_cast<const uint2*>(sd + tl * 256 + lane * 8);
+      const float4 st = sst[tl];
+      float d[4];
+      { float2 x = unpack_bf16x2(dr.x); d[0] = x.x; d[1] = x.y; x = unpack_bf16x2(dr.y); d[2] = x.x; d[3] = x.y; }
+      if (a.drop_p > 0.f) {
+        const uint32_t kb = static_cast<uint32_t>(skb[tl * 16 + (lane >> 1)]) >> kshift;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) d[e] = ((kb >> e) & 1u) ? d[e] * keep_scale : 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float ya = wa[e][0] * ua2[e] + wa[e][1] * ua1[e] + wa[e][2] * ua0[e];
+        const float yg = wg[e][0] * ug2[e] + wg[e][1] * ug1[e] + wg[e][2] * ug0[e];
+        float phi, pdf;
+        normal_cdf_pdf(yg, phi, pdf);
+        const float ge = yg * phi;
+        const float hhat = (ge * ya - st.x) * st.y;
+        const float gd = gm[e] * d[e];
+        const float dh = (gm[e] != 0.f) ? st.y * (gd - st.z - hhat * st.w) : 0.f;   // padded channels: gamma == 0
+        da0[e] = dh * ge;
+        dg0[e] = dh * ya * fmaf(yg, pdf, phi);
+        if (own) {
+          dgam[e] += d[e] * hhat;
+          dwa[e][0] += da0[e] * ua2[e]; dwa[e][1] += da0[e] * ua1[e]; dwa[e][2] += da0[e] * ua0[e];
+          dwg[e][0] += dg0[e] * ug2[e]; dwg[e][1] += dg0[e] * ug1[e]; dwg[e][2] += dg0[e] * ug0[e];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { da0[e] = 0.f; dg0[e] = 0.f; }
+    }
+    if (i >= 2 && tb + tl - 2 < a.N) {   // du[t-2] = w2 dy[t-2] + w1 dy[t-1] + w0 dy[t]
+      float oa[4], og[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        oa[e] = wa[e][2] * da2[e] + wa[e][1] * da1[e] + wa[e][0] * da0[e];
+        og[e] = wg[e][2] * dg2[e] + wg[e][1] * dg1[e] + wg[e][0] * dg0[e];
+      }
+      __nv_bfloat16* o = du_lane + static_cast<long>(i - 2) * ld;
+      *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(oa[0], oa[1]), pack_bf16x2(oa[2], oa[3]));
+      *reinterpret_cast<uint2*>(o + 128) = make_uint2(pack_bf16x2(og[0], og[1]), pack_bf16x2(og[2], og[3]));
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      ua2[e] = ua1[e]; ua1[e] = ua0[e]; ug2[e] = ug1[e]; ug1[e] = ug0[e];
+      da2[e] = da1[e]; da1[e] = da0[e]; dg2[e] = dg1[e]; dg1[e] = dg0[e];
+    }
+  }
+  // ---- weight gradients: warps combine in shared memory, one global atomic per (channel, tap) and CTA
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    atomicAdd(&sacc[lane * 4 + e], dgam[e]);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      atomicAdd(&dconv_w[(ca + i) * 3 + k], dwa[i][k]);
-      atomicAdd(&dconv_w[(ca + 128 + i) * 3 + k], dwg[i][k]);
+      atomicAdd(&sacc[(1 + k) * 128 + lane * 4 + e], dwa[e][k]);
+      atomicAdd(&sacc[(4 + k) * 128 + lane * 4 + e], dwg[e][k]);
     }
   }
+  __syncthreads();
+  for (int i = tid; i < 7 * 128; i += kTileThreads) {
+    const int q = i >> 7, c = i & 127;
+    const float v = sacc[i];
+    if (q == 0) atomicAdd(&dgamma[g * 128 + c], v);
+    else if (q < 4) atomicAdd(&dconv_w[(g * 256 + c) * 3 + (q - 1)], v);
+    else atomicAdd(&dconv_w[(g * 256 + 128 + c) * 3 + (q - 4)], v);
+  }
 }
-
 
 }  // namespace omlm
 
 extern "C" {
 
-int omlm_ffn_norm_fwd(const void* h, const float* rowsum, const float* gamma, void* hn, float* stats, long M, int F,
-                      int Fp, float drop_p, const unsigned long long* seed, int layer, void* stream) {
+int omlm_ffn_norm_fwd(const void* h, const float* rowsum, const float* gamma, void* hn, float* stats, void* keep_bits,
+                      long M, int F, int Fp, float drop_p, const unsigned long long* seed, int layer, void* stream) {
   using namespace omlm;
   OMLM_CHECK_ARG(M > 0 && F > 0 && Fp >= F && Fp % 128 == 0, "ffn_norm_fwd: bad shape F=%d Fp=%d", F, Fp);
-  OMLM_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || seed != nullptr), "ffn_norm_fwd: bad dropout args");
+  OMLM_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || (seed != nullptr && keep_bits != nullptr)),
+                 "ffn_norm_fwd: dropout needs a seed and a keep_bits buffer");
   ffn_norm_fwd_kernel<<<static_cast<int>((M + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(h), reinterpret_cast<const float2*>(rowsum), gamma,
-      reinterpret_cast<__nv_bfloat16*>(hn), reinterpret_cast<float2*>(stats), M, F, Fp, drop_p, seed,
-      static_cast<uint32_t>(layer));
+      reinterpret_cast<__nv_bfloat16*>(hn), reinterpret_cast<float2*>(stats), reinterpret_cast<uint8_t*>(keep_bits), M, F, Fp,
+      drop_p, seed, static_cast<uint32_t>(layer));
   OMLM_LAUNCH_CHECK();
   return 0;
 }
 
 int omlm_ffn_mid_bwd(const void* dhn, const void* hn, const void* u, const float* stats, const float* conv_w,
-                     const float* gamma, float* rowstat_scratch, void* du, float* dgamma, float* dconv_w, int B, int N,
-                     int F, int Fp, float drop_p, const unsigned long long* seed, int layer, void* stream) {
+                     const float* gamma, const void* keep_bits, float* rowstat_scratch, void* du, float* dgamma,
+                     float* dconv_w, int B, int N, int F, int Fp, float drop_p, void* stream) {
   using namespace omlm;
   OMLM_CHECK_ARG(B > 0 && N > 0 && F > 0 && Fp >= F && Fp % 128 == 0, "ffn_mid_bwd: bad shape F=%d Fp=%d", F, Fp);
+  OMLM_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || keep_bits != nullptr), "ffn_mid_bwd: dropout needs keep_bits");
   auto st = reinterpret_cast<cudaStream_t>(stream);
-  MidArgs a{reinterpret_cast<const __nv_bfloat16*>(u), conv_w, gamma, N, F, Fp, drop_p, seed, static_cast<uint32_t>(layer)};
+  MidArgs a{reinterpret_cast<const __nv_bfloat16*>(u), conv_w, gamma, N, F, Fp, drop_p, reinterpret_cast<const uint8_t*>(keep_bits)};
   const long M = static_cast<long>(B) * N;
   ffn_mid_bwd_stats_kernel<<<static_cast<int>((M + 7) / 8), 256, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(dhn), reinterpret_cast<const __nv_bfloat16*>(hn), gamma,
-      reinterpret_cast<float2*>(rowstat_scratch), M, F, Fp, drop_p, seed, static_cast<uint32_t>(layer));
+      reinterpret_cast<float2*>(rowstat_scratch), M, F, Fp, drop_p, a.keep_bits);
   OMLM_LAUNCH_CHECK();
-  const int rows_per_cta = 32;
-  dim3 grid(B * ((N + rows_per_cta - 1) / rows_per_cta), (Fp / kWalkCh + kWalkThreads - 1) / kWalkThreads);
-  ffn_mid_bwd_walk_kernel<<<grid, kWalkThreads, 0, st>>>(a, reinterpret_cast<const __nv_bfloat16*>(dhn),
-                                                         reinterpret_cast<const float2*>(stats),
-                                                         reinterpret_cast<const float2*>(rowstat_scratch),
-                                                         reinterpret_cast<__nv_bfloat16*>(du), dgamma, dconv_w, rows_per_cta);
+  static bool configured = false;
+  if (!configured) {
+    OMLM_CUDA(cudaFuncSetAttribute(ffn_mid_bwd_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem));
+    configured = true;
+  }
+  dim3 grid(B * ((N + kTileRows - 1) / kTileRows), Fp / 128);
+  ffn_mid_bwd_walk_kernel<<<grid, kTileThreads, kTileSmem, st>>>(a, reinterpret_cast<const __nv_bfloat16*>(dhn),
+                                                                reinterpret_cast<const float2*>(stats),
+                                                                reinterpret_cast<const float2*>(rowstat_scratch),
+                                                                reinterpret_cast<__nv_bfloat16*>(du), dgamma, dconv_w);
   OMLM_LAUNCH_CHECK();
   return 0;
 }

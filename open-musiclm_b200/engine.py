@@ -207,6 +207,7 @@ class Engine:
             o=[E(M, HD) for _ in range(nl)], lse=[E(M * h, dt=f32) for _ in range(nl)],
             xn2=[E(M, d) for _ in range(nl)], st_f=[E(M, 2, dt=f32) for _ in range(nl)],
             u=[E(M, 2 * Fp) for _ in range(nl)], hn=[E(M, Fp) for _ in range(nl)], st_i=[E(M, 2, dt=f32) for _ in range(nl)],
+            keep=[E(M, Fp // 8, dt=torch.uint8) for _ in range(nl)],   # FFN dropout keep mask, 1 bit per element
             xf=E(max(pl.rows_total, 1), d), st_o=E(M, 2, dt=f32), h=E(M, Fp), rowsum=E(M, 2, dt=f32),
             logits=[E(max(pl.B * c, 1), self.Cp[s], dt=f32) for (s, qi, c, b0) in pl.groups],
             # rel-pos MLP
@@ -286,7 +287,8 @@ class Engine:
             lib.layernorm_fwd(xm, pv[p + "2.0.gamma"], ws["xn2"][i], None, ws["st_f"][i])
             ws["rowsum"].zero_()
             lib.gemm_ffn_up(ws["xn2"][i], pk["w1"], pk["conv"], ws["u"][i], ws["h"], ws["rowsum"], N, Fp)   # conv + GEGLU in the epilogue
-            lib.ffn_norm_fwd(ws["h"], ws["rowsum"], pk["gin"], ws["hn"][i], ws["st_i"][i], F, Fp, drop_p, self.seed, l)
+            lib.ffn_norm_fwd(ws["h"], ws["rowsum"], pk["gin"], ws["hn"][i], ws["st_i"][i], F, Fp, drop_p, self.seed, l,
+                             keep_bits=ws["keep"][i] if drop_p > 0 else None)
             lib.gemm(ws["hn"][i], pk["w2"], xo, addend=xm, block_n=self._bn_for(M, d, Fp))
         x_last = x[2 * self.L] if train else x[0]
         lib.layernorm_fwd(x_last, pv["transformer.norm.gamma"], ws["xf"], None, ws["st_o"], pl.dest_row)
@@ -340,7 +342,7 @@ class Engine:
             self._wgrad(ws["dx_bf"], ws["hn"][l], gv[p + "2.6.weight"], d, Fp, n_valid=F)
             ws["dgin"].zero_(); ws["dconv"].zero_()
             lib.ffn_mid_bwd(ws["dhn"], ws["hn"][l], ws["u"][l], ws["st_i"][l], pk["conv"], pk["gin"], ws["rowstat"], ws["du"],
-                            ws["dgin"], ws["dconv"], B, N, F, Fp, drop_p, self.seed, l)
+                            ws["dgin"], ws["dconv"], B, N, F, Fp, drop_p, keep_bits=ws["keep"][l] if drop_p > 0 else None)
             lib.unpack_add(ws["dgin"], 1, Fp, gv[p + "2.4.gamma"], F, 1, F)
             lib.unpack_add(ws["dconv"], 2 * Fp, 3, gv[p + "2.2.ds_conv.weight"], 3, 2 * F, 3, split_dst=-1, split_src=F)
             lib.gemm(ws["du"], pk["w1"], ws["dxn"], b_mn=True, M=M, N=d, K=2 * Fp, block_n=self._bn_for(M, d, 2 * Fp))

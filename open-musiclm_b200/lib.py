@@ -212,14 +212,14 @@ def gemm_ffn_up(xn, w1_packed, conv_w_packed, u_out, h_out, rowsum, Nseq, Fp, ma
          _I(K), _I(Fp), _I(max_ctas), _stream())
 
 
-def ffn_norm_fwd(h, rowsum, gamma, hn, stats, F, Fp, drop_p=0.0, seed=None, layer=0):
-    call("omlm_ffn_norm_fwd", _p(h), _p(rowsum), _p(gamma), _p(hn), _p(stats), _L(h.shape[0]), _I(F), _I(Fp), _F(drop_p),
-         _p(seed), _I(layer), _stream())
+def ffn_norm_fwd(h, rowsum, gamma, hn, stats, F, Fp, drop_p=0.0, seed=None, layer=0, keep_bits=None):
+    call("omlm_ffn_norm_fwd", _p(h), _p(rowsum), _p(gamma), _p(hn), _p(stats), _p(keep_bits), _L(h.shape[0]), _I(F), _I(Fp),
+         _F(drop_p), _p(seed), _I(layer), _stream())
 
 
-def ffn_mid_bwd(dhn, hn, u, stats, conv_w, gamma, rowstat, du, dgamma, dconv_w, B, N, F, Fp, drop_p=0.0, seed=None, layer=0):
-    call("omlm_ffn_mid_bwd", _p(dhn), _p(hn), _p(u), _p(stats), _p(conv_w), _p(gamma), _p(rowstat), _p(du), _p(dgamma),
-         _p(dconv_w), _I(B), _I(N), _I(F), _I(Fp), _F(drop_p), _p(seed), _I(layer), _stream())
+def ffn_mid_bwd(dhn, hn, u, stats, conv_w, gamma, rowstat, du, dgamma, dconv_w, B, N, F, Fp, drop_p=0.0, keep_bits=None):
+    call("omlm_ffn_mid_bwd", _p(dhn), _p(hn), _p(u), _p(stats), _p(conv_w), _p(gamma), _p(keep_bits), _p(rowstat), _p(du),
+         _p(dgamma), _p(dconv_w), _I(B), _I(N), _I(F), _I(Fp), _F(drop_p), _stream())
 
 
 def cross_entropy(logits, labels, C, loss_acc, *, grad_scale=0.0, dlogits=None, ignore_index=-100, label_stride=1, rows=None):

@@ -263,7 +263,8 @@ def test_ffn_up_fused_and_mid_bwd(lib, B, N, d, F_, drop_p):
     lib.gemm_ffn_up(xn, w1p, cwp, u, h, rowsum, N, Fp)
     hn = torch.empty(M, Fp, device=DEV, dtype=torch.bfloat16); stats = torch.empty(M, 2, device=DEV)
     seed = torch.tensor([99], dtype=torch.int64, device=DEV)
-    lib.ffn_norm_fwd(h, rowsum, gp, hn, stats, F_, Fp, drop_p, seed, 3)
+    kbits = torch.zeros(M, Fp // 8, device=DEV, dtype=torch.uint8)
+    lib.ffn_norm_fwd(h, rowsum, gp, hn, stats, F_, Fp, drop_p, seed, 3, keep_bits=kbits if drop_p > 0 else None)
     torch.cuda.synchronize()
     # reference (the conv sees the bf16-rounded u, as in the unfused formulation)
     u_ref = (xn.float() @ W1.bfloat16().float().t())
@@ -278,7 +279,8 @@ def test_ffn_up_fused_and_mid_bwd(lib, B, N, d, F_, drop_p):
     assert rel(rowsum[:, 0], hmid.detach().reshape(M, F_).sum(1)) < 2e-3
     ref = F.layer_norm(hmid, (F_,), gr, None, 1e-5).reshape(M, F_)
     if drop_p > 0:
-        keep = (hn[:, :F_] != 0) | (ref.detach().abs() < 1e-3)
+        keep = ((kbits[:, :, None] >> torch.arange(8, device=DEV, dtype=torch.uint8)) & 1).bool().reshape(M, Fp)[:, :F_]
+        assert torch.equal(keep | (ref.detach().abs() < 1e-3), (hn[:, :F_] != 0) | (ref.detach().abs() < 1e-3))
         assert abs(1 - keep.float().mean().item() - drop_p) < 0.02
         ref = ref * keep / (1 - drop_p)
     assert float(hn[:, F_:].abs().max()) == 0
@@ -289,7 +291,7 @@ def test_ffn_up_fused_and_mid_bwd(lib, B, N, d, F_, drop_p):
     ref.backward(dhn[:, :F_].float())
     du = torch.empty(M, 2 * Fp, device=DEV, dtype=torch.bfloat16); rowstat = torch.empty(M, 2, device=DEV)
     dg = torch.zeros(Fp, device=DEV); dcw = torch.zeros(2 * Fp, 3, device=DEV)
-    lib.ffn_mid_bwd(dhn, hn, u, stats, cwp, gp, rowstat, du, dg, dcw, B, N, F_, Fp, drop_p, seed, 3)
+    lib.ffn_mid_bwd(dhn, hn, u, stats, cwp, gp, rowstat, du, dg, dcw, B, N, F_, Fp, drop_p, keep_bits=kbits if drop_p > 0 else None)
     assert rel(du[:, cols], uf.grad) < 1.5e-2
     assert rel(dg[:F_], gr.grad) < 8e-3
     dcw_c = torch.zeros(2 * F_, 3, device=DEV)

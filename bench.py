@@ -101,6 +101,39 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
+def usable_cores():
+    """Cores this process may actually use: scheduler affinity capped by the cgroup CPU quota (a container on a
+    128-core host often owns far fewer; asking torch for all visible cores then oversubscribes and crawls)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period) + 0.5)))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
+def pick_cpu_threads():
+    """Thread count with the best measured fp32 matmul throughput on this host (a few seconds of calibration on an
+    FFN-shaped product), so the CPU arm uses 'all the host threads it can use' rather than all it can see."""
+    import torch
+    top = usable_cores()
+    cands = sorted({c for c in (top, top // 2, top // 4, 64, 32, 16, 8) if 1 <= c <= top}, reverse=True)
+    a, b = torch.randn(2048, 1024), torch.randn(1024, 2730)
+    best, best_t = cands[-1], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        a @ b
+        t0 = time.perf_counter()
+        for _ in range(3):
+            a @ b
+        t = time.perf_counter() - t0
+        if t < best_t * 0.95:
+            best, best_t = c, t
+    return best
+
+
 def cpu_reference_arm(steps, warmup, budget_s=150.0):
     """The reference's own CPU path, as restated by the oracle (kind "port": /root/reference cannot travel to the
     GPU box): full coarse training step (forward, backward, clip 0.5, AdamW) in fp32 on all host cores, on a
@@ -108,7 +141,7 @@ def cpu_reference_arm(steps, warmup, budget_s=150.0):
     import numpy as np
     import torch
     from oracle import restatement as R
-    cores = os.cpu_count() or 1
+    cores = pick_cpu_threads()
     torch.set_num_threads(cores)
     cfg = R.coarse_cfg(ce_weights=TRAIN["ce_weights"])
     params = {k: v for k, v in R.init_state(cfg, seed=0).items()}
@@ -215,8 +248,19 @@ def run_b200(args):
         gemm_log.append((e0, e1, 2.0 * M * Nn * K))
         return r
     lib.gemm = timed_gemm
+    orig_ffn_up = lib.gemm_ffn_up
+
+    def timed_ffn_up(xn, w1p, cwp, u, h, rowsum, Nseq, Fp, **kw):   # the FFN-up GEMM (conv + GEGLU fused in its epilogue)
+        if not instrument["on"]:
+            return orig_ffn_up(xn, w1p, cwp, u, h, rowsum, Nseq, Fp, **kw)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); r = orig_ffn_up(xn, w1p, cwp, u, h, rowsum, Nseq, Fp, **kw); e1.record()
+        gemm_log.append((e0, e1, 2.0 * xn.shape[0] * (2 * Fp) * xn.shape[1]))
+        return r
+    lib.gemm_ffn_up = timed_ffn_up
     import open_musiclm_b200.engine as eng_mod
     eng_mod.lib.gemm = timed_gemm
+    eng_mod.lib.gemm_ffn_up = timed_ffn_up
 
     def sync_all():
         if world > 1:
@@ -293,7 +337,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": 4},
             "gpu_launches": n_launch * args.steps, "gpu_launches_per_step": n_launch,
             "launch_mode": "step replayed from two CUDA graphs (fwd+bwd | clip+AdamW+pack), NCCL all-reduce eager between them" if tr.use_cuda_graph else "eager launches",
-            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all operand-major variants)", "achieved": ach,
+            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel + gemm_ffn_up_kernel (tcgen05; all operand-major variants; FFN-up time includes its fused conv+GEGLU epilogue)", "achieved": ach,
                          "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": ach / peaks["sustained"], "traffic": None,
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']})",
                          "launches_per_step": n_gemm, "gemm_ms_per_step": g_ms / args.steps,

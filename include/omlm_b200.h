@@ -151,6 +151,15 @@ int omlm_cross_entropy(const float* logits, long ld, const int* labels, int labe
 int omlm_grad_sumsq(const float* g, long n, float prescale, double* acc, void* stream);
 int omlm_adamw_step(float* p, const float* g, float* m, float* v, long n, long n_decay, const float* hyper,
                     const double* sumsq, void* stream);
+/* One launch for a whole table of omlm_pack jobs (the per-step refresh of the packed bf16 weights).  The table is
+ * DEVICE memory; unit_start = running sum of ceil(rows_p * ceil(cols_p/4) / 256) over the preceding jobs,
+ * total_units = that sum over all jobs.  njobs <= 64. */
+typedef struct {
+  const float* src; void* dst;
+  long src_ld, dst_ld, unit_start;
+  int rows_valid, cols_valid, rows_p, cols_p, split_dst, split_src, dst_f32, reserved;
+} omlm_pack_job;
+int omlm_pack_multi(const omlm_pack_job* jobs_device, int njobs, long total_units, void* stream);
 /* canonical fp32 -> padded compute layout (bf16 or fp32) and gradient unpacking (+=). */
 int omlm_pack(const float* src, long src_ld, int rows_valid, int cols_valid, void* dst, int dst_f32, long dst_ld,
               int rows_p, int cols_p, int split_dst, int split_src, void* stream);

@@ -4,6 +4,7 @@
 // Replaces  LayerNorm.forward        open_musiclm/transformer.py:24-31  (F.layer_norm, eps 1e-5, beta == 0)
 //           l2norm + q/k scale        open_musiclm/transformer.py:269-271, utils.py:68-69
 #include "common.cuh"
+#include <algorithm>
 #include "../../include/omlm_b200.h"
 
 namespace omlm {
@@ -69,47 +70,90 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
 // LayerNorm backward.  dx = [dres] + [draw] + rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat))
 // dgamma[col] += sum_rows dy * xhat  (fp32; per-block partials in smem, one global atomic per column per block).
 // dy rows may be permuted (src_row: row of dy for this x row, -1 = no gradient).
-// Two passes per row with a re-read (the 6 KB row is L1-resident) instead of caching xhat / g*dy in registers:
-// ~64 registers per thread -> 4 blocks (32 warps) per SM, which is what hides the HBM latency here.
-template <int NCHUNK>
-__global__ void __launch_bounds__(kNormThreads, 3)
+// One warp per row.  The row's operands (x, dy, dres, draw: up to 12 bytes per element) are brought to a per-warp,
+// double-buffered shared-memory stage with cp.async, so a warp always has the whole NEXT row in flight while it
+// reduces the current one: bytes in flight per SM (~100 KB) are set by shared memory, not by registers.  Every lane
+// reads back only the bytes it copied itself, so no barrier is needed beyond cp.async.wait_group.
+__device__ __forceinline__ void ln_cp16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ln_cp8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
+}
+
+template <int NCHUNK, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
                      const float2* __restrict__ stats, const float* __restrict__ gamma,
                      const float* __restrict__ dres, const __nv_bfloat16* __restrict__ draw,
                      const int* __restrict__ src_row, float* __restrict__ dx,
                      __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, int M, int D,
                      int rows_per_block) {
-  __shared__ float sdg[NCHUNK * 128];
+  constexpr int kRow = NCHUNK * 128;                 // padded row length in elements
+  constexpr int kStage = kRow * 12;                  // x fp32 | dres fp32 | dy bf16 | draw bf16
+  extern __shared__ __align__(16) uint8_t lsm[];
+  float* sdg = reinterpret_cast<float*>(lsm + WARPS * 2 * kStage);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < NCHUNK * 128; i += kNormThreads) sdg[i] = 0.f;
+  for (int i = threadIdx.x; i < kRow; i += WARPS * 32) sdg[i] = 0.f;
   __syncthreads();
-  float4 dg[NCHUNK];
+  uint8_t* wbuf = lsm + warp * 2 * kStage;
+  float4 dg[NCHUNK], gm[NCHUNK];
 #pragma unroll
-  for (int c = 0; c < NCHUNK; ++c) dg[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = 0; c < NCHUNK; ++c) {
+    dg[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int col = (c * 32 + lane) * 4;
+    gm[c] = col < D ? *reinterpret_cast<const float4*>(gamma + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   const int row0 = blockIdx.x * rows_per_block;
   const int row1 = min(M, row0 + rows_per_block);
-  for (int row = row0 + warp; row < row1; row += kNormThreads / 32) {
-    const float2 st = stats[row];
-    const float* xr = x + static_cast<long long>(row) * D;
-    long long drow = row;
-    if (src_row != nullptr) drow = src_row[row];
-    const __nv_bfloat16* dyr = dy + (drow < 0 ? 0 : drow) * D;
-    float s1 = 0.f, s2 = 0.f;
-    if (drow >= 0) {
+  auto src_of = [&](int r) -> long long { return (r < row1) ? (src_row != nullptr ? static_cast<long long>(src_row[r]) : r) : -1; };
+  auto issue = [&](int r, long long drow, int stage) {
+    uint8_t* sb = wbuf + stage * kStage;
+    const float* xr = x + static_cast<long long>(r) * D;
 #pragma unroll
-      for (int c = 0; c < NCHUNK; ++c) {
-        const int col = (c * 32 + lane) * 4;
-        if (col < D) {
-          const float4 xv = *reinterpret_cast<const float4*>(xr + col);
-          const uint2 dv = *reinterpret_cast<const uint2*>(dyr + col);
-          const float4 g = *reinterpret_cast<const float4*>(gamma + col);
-          const float2 d01 = unpack_bf16x2(dv.x), d23 = unpack_bf16x2(dv.y);
-          const float h0 = (xv.x - st.x) * st.y, h1 = (xv.y - st.x) * st.y, h2 = (xv.z - st.x) * st.y, h3 = (xv.w - st.x) * st.y;
-          dg[c].x += d01.x * h0; dg[c].y += d01.y * h1; dg[c].z += d23.x * h2; dg[c].w += d23.y * h3;
-          const float g0 = d01.x * g.x, g1 = d01.y * g.y, g2 = d23.x * g.z, g3 = d23.y * g.w;
-          s1 += g0 + g1 + g2 + g3;
-          s2 += g0 * h0 + g1 * h1 + g2 * h2 + g3 * h3;
-        }
+    for (int c = 0; c < NCHUNK; ++c) {
+      const int col = (c * 32 + lane) * 4;
+      if (col < D) {
+        ln_cp16(sb + col * 4, xr + col);
+        if (dres != nullptr) ln_cp16(sb + kRow * 4 + col * 4, dres + static_cast<long long>(r) * D + col);
+        if (drow >= 0) ln_cp8(sb + kRow * 8 + col * 2, dy + drow * D + col);
+        if (draw != nullptr) ln_cp8(sb + kRow * 10 + col * 2, draw + static_cast<long long>(r) * D + col);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int row = row0 + warp;
+  long long d_cur = src_of(row), d_nxt = src_of(row + WARPS);
+  float2 st_nxt = make_float2(0.f, 0.f);
+  if (row < row1) { issue(row, d_cur, 0); st_nxt = stats[row]; }
+  int stage = 0;
+  for (; row < row1; row += WARPS, stage ^= 1) {
+    const float2 st = st_nxt;
+    const long long d_nn = src_of(row + 2 * WARPS);     // two rows ahead: ready when its copies are issued
+    if (row + WARPS < row1) {
+      issue(row + WARPS, d_nxt, stage ^ 1);
+      st_nxt = stats[row + WARPS];
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    const uint8_t* sb = wbuf + stage * kStage;
+    float4 hh[NCHUNK], gg[NCHUNK];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) {
+      const int col = (c * 32 + lane) * 4;
+      hh[c] = make_float4(0.f, 0.f, 0.f, 0.f); gg[c] = hh[c];
+      if (col < D && d_cur >= 0) {
+        const float4 xv = *reinterpret_cast<const float4*>(sb + col * 4);
+        const uint2 dv = *reinterpret_cast<const uint2*>(sb + kRow * 8 + col * 2);
+        const float2 d01 = unpack_bf16x2(dv.x), d23 = unpack_bf16x2(dv.y);
+        const float h0 = (xv.x - st.x) * st.y, h1 = (xv.y - st.x) * st.y, h2 = (xv.z - st.x) * st.y, h3 = (xv.w - st.x) * st.y;
+        dg[c].x += d01.x * h0; dg[c].y += d01.y * h1; dg[c].z += d23.x * h2; dg[c].w += d23.y * h3;
+        const float g0 = d01.x * gm[c].x, g1 = d01.y * gm[c].y, g2 = d23.x * gm[c].z, g3 = d23.y * gm[c].w;
+        s1 += g0 + g1 + g2 + g3;
+        s2 += g0 * h0 + g1 * h1 + g2 * h2 + g3 * h3;
+        hh[c] = make_float4(h0, h1, h2, h3); gg[c] = make_float4(g0, g1, g2, g3);
       }
     }
     s1 = warp_sum(s1) / D;
@@ -119,22 +163,18 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
       const int col = (c * 32 + lane) * 4;
       if (col < D) {
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (drow >= 0) {
-          const float4 xv = *reinterpret_cast<const float4*>(xr + col);           // L1 hit
-          const uint2 dv = *reinterpret_cast<const uint2*>(dyr + col);
-          const float4 g = *reinterpret_cast<const float4*>(gamma + col);
-          const float2 d01 = unpack_bf16x2(dv.x), d23 = unpack_bf16x2(dv.y);
-          o.x = st.y * (d01.x * g.x - s1 - (xv.x - st.x) * st.y * s2);
-          o.y = st.y * (d01.y * g.y - s1 - (xv.y - st.x) * st.y * s2);
-          o.z = st.y * (d23.x * g.z - s1 - (xv.z - st.x) * st.y * s2);
-          o.w = st.y * (d23.y * g.w - s1 - (xv.w - st.x) * st.y * s2);
+        if (d_cur >= 0) {
+          o.x = st.y * (gg[c].x - s1 - hh[c].x * s2);
+          o.y = st.y * (gg[c].y - s1 - hh[c].y * s2);
+          o.z = st.y * (gg[c].z - s1 - hh[c].z * s2);
+          o.w = st.y * (gg[c].w - s1 - hh[c].w * s2);
         }
         if (dres != nullptr) {
-          const float4 r = *reinterpret_cast<const float4*>(dres + static_cast<long long>(row) * D + col);
+          const float4 r = *reinterpret_cast<const float4*>(sb + kRow * 4 + col * 4);
           o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
         }
         if (draw != nullptr) {
-          const uint2 rv = *reinterpret_cast<const uint2*>(draw + static_cast<long long>(row) * D + col);
+          const uint2 rv = *reinterpret_cast<const uint2*>(sb + kRow * 10 + col * 2);
           const float2 r01 = unpack_bf16x2(rv.x), r23 = unpack_bf16x2(rv.y);
           o.x += r01.x; o.y += r01.y; o.z += r23.x; o.w += r23.y;
         }
@@ -147,6 +187,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
         }
       }
     }
+    d_cur = d_nxt; d_nxt = d_nn;
   }
 #pragma unroll
   for (int c = 0; c < NCHUNK; ++c) {
@@ -157,7 +198,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
     atomicAdd(&sdg[col + 3], dg[c].w);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < D; i += kNormThreads) atomicAdd(&dgamma[i], sdg[i]);
+  for (int i = threadIdx.x; i < D; i += WARPS * 32) atomicAdd(&dgamma[i], sdg[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -321,13 +362,21 @@ template <int NCHUNK>
 static int launch_ln_bwd(const __nv_bfloat16* dy, const float* x, const float2* stats, const float* gamma,
                          const float* dres, const __nv_bfloat16* draw, const int* src_row, float* dx,
                          __nv_bfloat16* dx_bf16, float* dgamma, int M, int D, cudaStream_t st) {
-  // ~2 waves of 3 resident blocks per SM; each block walks a contiguous slab of rows and flushes dgamma once.
-  int blocks = num_sms() * 6;
+  // shared memory (2 stages of 12 B/element per warp) decides residency: 8 warps up to D = 1024, 4 above
+  constexpr int WARPS = NCHUNK <= 8 ? 8 : 4;
+  constexpr int smem = WARPS * 2 * NCHUNK * 128 * 12 + NCHUNK * 128 * 4;
+  static bool configured = false;
+  if (!configured) {
+    OMLM_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<NCHUNK, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int per_sm = std::max(1, std::min(4, (220 * 1024) / smem));
+  int blocks = num_sms() * per_sm;
   int rows_per_block = (M + blocks - 1) / blocks;
-  if (rows_per_block < 8) rows_per_block = 8;
+  if (rows_per_block < WARPS) rows_per_block = WARPS;
   blocks = (M + rows_per_block - 1) / rows_per_block;
-  layernorm_bwd_kernel<NCHUNK><<<blocks, kNormThreads, 0, st>>>(dy, x, stats, gamma, dres, draw, src_row, dx,
-                                                               dx_bf16, dgamma, M, D, rows_per_block);
+  layernorm_bwd_kernel<NCHUNK, WARPS><<<blocks, WARPS * 32, smem, st>>>(dy, x, stats, gamma, dres, draw, src_row, dx,
+                                                                       dx_bf16, dgamma, M, D, rows_per_block);
   OMLM_LAUNCH_CHECK();
   return 0;
 }

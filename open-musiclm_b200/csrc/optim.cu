@@ -65,44 +65,68 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
 //                     w = r % 256, c = (r / 256) * 128 + w % 128, src row = (w / 128) * split_src + c, live iff c < split_src
 //      split_dst = 0: live iff r < rows_valid.
 template <typename OutT>
-__global__ void pack_kernel(const float* __restrict__ src, long src_ld, int rows_valid, int cols_valid,
-                            OutT* __restrict__ dst, long dst_ld, int rows_p, int cols_p, int split_dst, int split_src) {
-  // one thread per 4 consecutive columns of a destination row
+__device__ __forceinline__ void pack_quad(long i, const float* __restrict__ src, long src_ld, int rows_valid, int cols_valid,
+                                          OutT* __restrict__ dst, long dst_ld, int cols_p, int split_dst, int split_src) {
+  // one call per 4 consecutive columns of a destination row
   const int c4n = (cols_p + 3) >> 2;
-  const long total = static_cast<long>(rows_p) * c4n;
   const bool vec_src = ((src_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
   const bool vec_dst = ((dst_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((cols_p & 3) == 0);
-  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(i / c4n), c = static_cast<int>(i - static_cast<long>(r) * c4n) << 2;
-    int sr = r; bool live = r < rows_valid;
-    if (split_dst > 0) { const int half = r / split_dst, rr = r - half * split_dst; sr = half * split_src + rr; live = rr < split_src && sr < rows_valid; }
-    else if (split_dst < 0) { const int w = r & 255, c = ((r >> 8) << 7) + (w & 127); sr = (w >> 7) * split_src + c; live = c < split_src && sr < rows_valid; }
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (live) {
-      if (vec_src && c + 3 < cols_valid) {
-        const float4 t = *reinterpret_cast<const float4*>(src + sr * src_ld + c);
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) if (c + j < cols_valid) v[j] = src[sr * src_ld + c + j];
-      }
-    }
-    OutT* d = dst + r * dst_ld + c;
-    if (vec_dst) {
-      if constexpr (sizeof(OutT) == 2) {
-        uint2 o; o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-        *reinterpret_cast<uint2*>(d) = o;
-      } else {
-        *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
-      }
+  const int r = static_cast<int>(i / c4n), c = static_cast<int>(i - static_cast<long>(r) * c4n) << 2;
+  int sr = r; bool live = r < rows_valid;
+  if (split_dst > 0) { const int half = r / split_dst, rr = r - half * split_dst; sr = half * split_src + rr; live = rr < split_src && sr < rows_valid; }
+  else if (split_dst < 0) { const int w = r & 255, ch = ((r >> 8) << 7) + (w & 127); sr = (w >> 7) * split_src + ch; live = ch < split_src && sr < rows_valid; }
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (live) {
+    if (vec_src && c + 3 < cols_valid) {
+      const float4 t = *reinterpret_cast<const float4*>(src + sr * src_ld + c);
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (c + j < cols_p) {
-          if constexpr (sizeof(OutT) == 2) d[j] = __float2bfloat16_rn(v[j]); else d[j] = v[j];
-        }
+      for (int j = 0; j < 4; ++j) if (c + j < cols_valid) v[j] = src[sr * src_ld + c + j];
+    }
+  }
+  OutT* d = dst + r * dst_ld + c;
+  if (vec_dst) {
+    if constexpr (sizeof(OutT) == 2) {
+      uint2 o; o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+      *reinterpret_cast<uint2*>(d) = o;
+    } else {
+      *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (c + j < cols_p) {
+        if constexpr (sizeof(OutT) == 2) d[j] = __float2bfloat16_rn(v[j]); else d[j] = v[j];
       }
     }
+  }
+}
+
+template <typename OutT>
+__global__ void pack_kernel(const float* __restrict__ src, long src_ld, int rows_valid, int cols_valid,
+                            OutT* __restrict__ dst, long dst_ld, int rows_p, int cols_p, int split_dst, int split_src) {
+  const long total = static_cast<long>(rows_p) * ((cols_p + 3) >> 2);
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x)
+    pack_quad<OutT>(i, src, src_ld, rows_valid, cols_valid, dst, dst_ld, cols_p, split_dst, split_src);
+}
+
+// All repacks of one optimiser step in ONE launch: the job table lives in device memory, work is cut into units of
+// 256 quads and blocks stride over the concatenated unit list (45 small launches -> 1 bandwidth-bound pass).
+__global__ void __launch_bounds__(256) pack_multi_kernel(const omlm_pack_job* __restrict__ jobs, int njobs, long total_units) {
+  __shared__ long starts[65];
+  for (int j = threadIdx.x; j < njobs; j += blockDim.x) starts[j] = jobs[j].unit_start;
+  if (threadIdx.x == 0) starts[njobs] = total_units;
+  __syncthreads();
+  for (long u = blockIdx.x; u < total_units; u += gridDim.x) {
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (starts[mid] <= u) lo = mid; else hi = mid - 1; }
+    const omlm_pack_job jb = jobs[lo];
+    const long i = (u - jb.unit_start) * 256 + threadIdx.x;
+    const long total = static_cast<long>(jb.rows_p) * ((jb.cols_p + 3) >> 2);
+    if (i >= total) continue;
+    if (jb.dst_f32) pack_quad<float>(i, jb.src, jb.src_ld, jb.rows_valid, jb.cols_valid, reinterpret_cast<float*>(jb.dst), jb.dst_ld, jb.cols_p, jb.split_dst, jb.split_src);
+    else pack_quad<__nv_bfloat16>(i, jb.src, jb.src_ld, jb.rows_valid, jb.cols_valid, reinterpret_cast<__nv_bfloat16*>(jb.dst), jb.dst_ld, jb.cols_p, jb.split_dst, jb.split_src);
   }
 }
 
@@ -155,6 +179,15 @@ int omlm_pack(const float* src, long src_ld, int rows_valid, int cols_valid, voi
     pack_kernel<float><<<blocks, 256, 0, st>>>(src, src_ld, rows_valid, cols_valid, reinterpret_cast<float*>(dst), dst_ld, rows_p, cols_p, split_dst, split_src);
   else
     pack_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(src, src_ld, rows_valid, cols_valid, reinterpret_cast<__nv_bfloat16*>(dst), dst_ld, rows_p, cols_p, split_dst, split_src);
+  OMLM_LAUNCH_CHECK();
+  return 0;
+}
+
+int omlm_pack_multi(const omlm_pack_job* jobs_device, int njobs, long total_units, void* stream) {
+  using namespace omlm;
+  OMLM_CHECK_ARG(jobs_device != nullptr && njobs > 0 && njobs <= 64 && total_units > 0, "pack_multi: need 1..64 jobs");
+  const int blocks = static_cast<int>(std::min<long>(total_units, static_cast<long>(num_sms()) * 16));
+  pack_multi_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(jobs_device, njobs, total_units);
   OMLM_LAUNCH_CHECK();
   return 0;
 }

@@ -159,6 +159,7 @@ class Engine:
                 w2=torch.empty(d, Fp, device=dev, dtype=bf), conv=torch.empty(2 * Fp, 3, device=dev),
                 gin=torch.empty(Fp, device=dev)))
         self.pk_logit = [torch.empty(s.num_quantizers, cp, d, device=dev, dtype=bf) for s, cp in zip(self.seqs, self.Cp)]
+        self._pack_table = None
         self.pk_rp = [torch.empty(self.Hr, 3 * self.Hr, device=dev, dtype=bf) for _ in range(2)]   # rel-pos MLP layers 1, 2: [hi|lo|hi]
 
     def refresh_packed(self, force=False):
@@ -167,19 +168,23 @@ class Engine:
             return
         d, HD, F, Fp = self.d, self.HD, self.F, self.Fp
         pv = self.pview
-        for l, pk in enumerate(self.pk):
-            p = f"transformer.layers.{l}."
-            lib.pack(pv[p + "0.to_q.weight"], d, HD, d, pk["wq"], HD, d)
-            lib.pack(pv[p + "0.to_kv.weight"], d, 128, d, pk["wkv"], 128, d)
-            lib.pack(pv[p + "0.to_out.0.weight"], HD, d, HD, pk["wo"], d, HD)
-            lib.pack(pv[p + "2.1.weight"], d, 2 * F, d, pk["w1"], 2 * Fp, d, split_dst=-1, split_src=F)
-            lib.pack(pv[p + "2.6.weight"], F, d, F, pk["w2"], d, Fp)
-            lib.pack(pv[p + "2.2.ds_conv.weight"], 3, 2 * F, 3, pk["conv"], 2 * Fp, 3, split_dst=-1, split_src=F)
-            lib.pack(pv[p + "2.4.gamma"], F, 1, F, pk["gin"], 1, Fp)
-        for s, seq in enumerate(self.seqs):
-            # [q, C, d] -> [q, Cp, d]: every head padded with zero rows
-            lib.pack(pv[f"logit_weights.{s}"], d, seq.num_quantizers * self.C[s], d, self.pk_logit[s].view(-1, d),
-                     seq.num_quantizers * self.Cp[s], d, split_dst=self.Cp[s], split_src=self.C[s])
+        if self._pack_table is None:      # the job table is built once: arena views and packed buffers never move
+            tab = lib.PackTable(self.dev)
+            for l, pk in enumerate(self.pk):
+                p = f"transformer.layers.{l}."
+                tab.add(pv[p + "0.to_q.weight"], d, HD, d, pk["wq"], HD, d)
+                tab.add(pv[p + "0.to_kv.weight"], d, 128, d, pk["wkv"], 128, d)
+                tab.add(pv[p + "0.to_out.0.weight"], HD, d, HD, pk["wo"], d, HD)
+                tab.add(pv[p + "2.1.weight"], d, 2 * F, d, pk["w1"], 2 * Fp, d, split_dst=-1, split_src=F)
+                tab.add(pv[p + "2.6.weight"], F, d, F, pk["w2"], d, Fp)
+                tab.add(pv[p + "2.2.ds_conv.weight"], 3, 2 * F, 3, pk["conv"], 2 * Fp, 3, split_dst=-1, split_src=F)
+                tab.add(pv[p + "2.4.gamma"], F, 1, F, pk["gin"], 1, Fp)
+            for s, seq in enumerate(self.seqs):
+                # [q, C, d] -> [q, Cp, d]: every head padded with zero rows
+                tab.add(pv[f"logit_weights.{s}"], d, seq.num_quantizers * self.C[s], d, self.pk_logit[s].view(-1, d),
+                         seq.num_quantizers * self.Cp[s], d, split_dst=self.Cp[s], split_src=self.C[s])
+            self._pack_table = tab
+        self._pack_table.run()
         for j in (1, 2):
             lib.split3_bf16(pv[f"transformer.rel_pos_bias.net.{j}.0.weight"], self.pk_rp[j - 1], weight_mode=True)
         self._packed_version = ver
@@ -263,7 +268,9 @@ class Engine:
             lib.split3_bf16(ws["rp_a"][j - 1], ws["rp_a3"][j - 1])
             lib.gemm(ws["rp_a3"][j - 1], self.pk_rp[j - 1], ws["rp_z"][j], block_n=128)
             lib.bias_silu(ws["rp_z"][j], pv[f"{pre}{j}.0.bias"], ws["rp_a"][j])
-        lib.sgemm_small(ws["rp_a"][2], (Hr, 1), pv[pre + "3.weight"], (1, Hr), ws["table"], (1, N), N, h, Hr, bias=pv[pre + "3.bias"])
+        ws["table"].zero_()      # split-K accumulate: 16 CTAs with a 512-long reduction each would leave the GPU idle
+        lib.sgemm_small(ws["rp_a"][2], (Hr, 1), pv[pre + "3.weight"], (1, Hr), ws["table"], (1, N), N, h, Hr, bias=pv[pre + "3.bias"],
+                        accumulate=True)
 
     def forward_core(self, pl: _Plan, ws, src_row, key_mask, train: bool, groups_wanted=None, drop: bool = False):
         """Runs embeddings -> depth x (attention, conv-FFN) -> final LN -> logit heads.  Activations stay in `ws`."""

@@ -242,6 +242,36 @@ def pack(src, src_ld, rows_valid, cols_valid, dst, rows_p, cols_p, split_dst=0, 
          _L(cols_p if dst.dim() == 1 else dst.stride(0)), _I(rows_p), _I(cols_p), _I(split_dst), _I(split_src), _stream())
 
 
+class _PackJob(ctypes.Structure):
+    _fields_ = [("src", ctypes.c_void_p), ("dst", ctypes.c_void_p), ("src_ld", ctypes.c_long), ("dst_ld", ctypes.c_long),
+                ("unit_start", ctypes.c_long), ("rows_valid", ctypes.c_int), ("cols_valid", ctypes.c_int),
+                ("rows_p", ctypes.c_int), ("cols_p", ctypes.c_int), ("split_dst", ctypes.c_int), ("split_src", ctypes.c_int),
+                ("dst_f32", ctypes.c_int), ("reserved", ctypes.c_int)]
+
+
+class PackTable:
+    """Device-resident table of pack jobs (same arguments as pack()); run() repacks all of them in one launch."""
+
+    def __init__(self, device):
+        self.device, self.jobs, self.keep, self.units, self.table = device, [], [], 0, None
+
+    def add(self, src, src_ld, rows_valid, cols_valid, dst, rows_p, cols_p, split_dst=0, split_src=0):
+        dst_ld = cols_p if dst.dim() == 1 else dst.stride(0)
+        self.jobs.append(_PackJob(src.data_ptr(), dst.data_ptr(), src_ld, dst_ld, self.units, rows_valid, cols_valid, rows_p,
+                                  cols_p, split_dst, split_src, int(dst.dtype == torch.float32), 0))
+        self.keep.append((src, dst))
+        self.units += (rows_p * ((cols_p + 3) // 4) + 255) // 256
+        self.table = None
+
+    def run(self):
+        if self.table is None:
+            arr = (_PackJob * len(self.jobs))(*self.jobs)
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            self.table = host.to(self.device)
+        assert 0 < len(self.jobs) <= 64, "omlm_pack_multi takes at most 64 jobs per table"
+        call("omlm_pack_multi", ctypes.c_void_p(self.table.data_ptr()), _I(len(self.jobs)), _L(self.units), _stream())
+
+
 def unpack_add(packed, rows_p, cols_p, dst, dst_ld, rows_valid, cols_valid, split_dst=0, split_src=0):
     call("omlm_unpack_add", _p(packed), _L(cols_p if packed.dim() == 1 else packed.stride(0)), _I(rows_p), _I(cols_p),
          _p(dst), _L(dst_ld), _I(rows_valid), _I(cols_valid), _I(split_dst), _I(split_src), _stream())

@@ -64,24 +64,75 @@ __device__ __forceinline__ float bf16_round(float x) {
 
 // ---- GELU (exact erf) ------------------------------------------------------------------------
 // Exact-erf GELU pieces from ONE exponential: e = exp(-x^2/2) gives both the normal pdf and, through the
+// ---- packed fp32x2 arithmetic (sm_100 FFMA2 / FMUL2 / FADD2: two independent fp32 operations per issued
+// instruction).  The SIMT kernels here are issue-bound on element-wise fp32 math, so pairing neighbouring channels
+// halves their floating-point instruction count.  Same IEEE round-to-nearest results as the scalar forms.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rc, rd;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n mov.b64 rc, {%6, %7};\n"
+      " fma.rn.f32x2 rd, ra, rb, rc;\n mov.b64 {%0, %1}, rd;}\n"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n mul.rn.f32x2 rd, ra, rb;\n mov.b64 {%0, %1}, rd;}\n"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n add.rn.f32x2 rd, ra, rb;\n mov.b64 {%0, %1}, rd;}\n"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP, <= 1 ulp, no slow path
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // Abramowitz-Stegun 7.1.26 rational form (|error| <= 1.5e-7, below fp32 resolution of the products here),
 // erf(x/sqrt(2)).  cdf = Phi(x), pdf = phi(x);  gelu(x) = x*cdf, gelu'(x) = cdf + x*pdf.
 __device__ __forceinline__ void normal_cdf_pdf(float x, float& cdf, float& pdf) {
-  const float e = __expf(-0.5f * x * x);
-  const float ax = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float half_erfc = 0.5f * p * t * e;            // 0.5 * erfc(|x|/sqrt2)
+  const float e = ex2_approx(-0.72134752044448170f * x * x);          // exp(-x^2/2)
+  const float t = rcp_approx(fmaf(0.23164189f, fabsf(x), 1.f));        // 0.3275911 / sqrt(2)
+  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);        // the 1/2 of erfc/2 folded into the coefficients
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  const float half_erfc = p * t * e;                    // 0.5 * erfc(|x|/sqrt2)
   cdf = x >= 0.f ? 1.f - half_erfc : half_erfc;
   pdf = 0.3989422804014327f * e;
+}
+// the same on two channels at once
+__device__ __forceinline__ void normal_cdf_pdf2(float2 x, float2& cdf, float2& pdf) {
+  const float2 q = mul2(mul2(x, x), splat2(-0.72134752044448170f));
+  const float2 e = make_float2(ex2_approx(q.x), ex2_approx(q.y));
+  const float2 t = make_float2(rcp_approx(fmaf(0.23164189f, fabsf(x.x), 1.f)), rcp_approx(fmaf(0.23164189f, fabsf(x.y), 1.f)));
+  float2 p = fma2(splat2(0.5f * 1.061405429f), t, splat2(0.5f * -1.453152027f));
+  p = fma2(p, t, splat2(0.5f * 1.421413741f));
+  p = fma2(p, t, splat2(0.5f * -0.284496736f));
+  p = fma2(p, t, splat2(0.5f * 0.254829592f));
+  const float2 h = mul2(mul2(p, t), e);
+  cdf = make_float2(x.x >= 0.f ? 1.f - h.x : h.x, x.y >= 0.f ? 1.f - h.y : h.y);
+  pdf = mul2(e, splat2(0.3989422804014327f));
 }
 __device__ __forceinline__ float gelu_erf(float x) {
   float c, p;
   normal_cdf_pdf(x, c, p);
   return x * c;
+}
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+  float2 c, p;
+  normal_cdf_pdf2(x, c, p);
+  return mul2(x, c);
 }
 
 // Philox-4x32 counter RNG, 7 rounds (the shortest variant that passes BigCrush): dropout / forgetful-mask

@@ -208,9 +208,9 @@ ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, 
   asm volatile("cp.async.commit_group;" ::: "memory");
   for (int i = tid; i < 7 * 128; i += kTileThreads) sacc[i] = 0.f;
 
-  // ---- per-lane constants: 4 value + 4 gate channels
+  // ---- per-lane constants: 4 value + 4 gate channels, held as two fp32x2 pairs (channels 2q, 2q+1)
   const int c0 = g * 128 + lane * 4;                   // natural channel index of this lane's first channel
-  float wa[4][3], wg[4][3], gm[4];
+  float2 wa[3][2], wg[3][2], gm[2], pm[2];             // taps [k][pair], gamma, 1/0 mask of real (un-padded) channels
   {
     const float4* wp = reinterpret_cast<const float4*>(a.conv_w + static_cast<long>(g * 256 + lane * 4) * 3);
     const float4* gp = reinterpret_cast<const float4*>(a.conv_w + static_cast<long>(g * 256 + 128 + lane * 4) * 3);
@@ -219,11 +219,16 @@ ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, 
     const float fa[12] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
     const float fb[12] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
 #pragma unroll
-    for (int e = 0; e < 4; ++e)
+    for (int k = 0; k < 3; ++k)
 #pragma unroll
-      for (int k = 0; k < 3; ++k) { wa[e][k] = fa[e * 3 + k]; wg[e][k] = fb[e * 3 + k]; }
-    const float4 gg = __ldg(reinterpret_cast<const float4*>(a.gamma + c0));
-    gm[0] = gg.x; gm[1] = gg.y; gm[2] = gg.z; gm[3] = gg.w;      // zero in the padding -> padded channels give dh = 0
+      for (int q = 0; q < 2; ++q) {
+        wa[k][q] = make_float2(fa[(2 * q) * 3 + k], fa[(2 * q + 1) * 3 + k]);
+        wg[k][q] = make_float2(fb[(2 * q) * 3 + k], fb[(2 * q + 1) * 3 + k]);
+      }
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(a.gamma + c0));   // zero in the padding
+    gm[0] = make_float2(gg.x, gg.y); gm[1] = make_float2(gg.z, gg.w);
+    pm[0] = make_float2(gg.x != 0.f ? 1.f : 0.f, gg.y != 0.f ? 1.f : 0.f);
+    pm[1] = make_float2(gg.z != 0.f ? 1.f : 0.f, gg.w != 0.f ? 1.f : 0.f);
   }
   const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
   asm volatile("cp.async.wait_all;" ::: "memory");
@@ -231,25 +236,20 @@ ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, 
 
   // ---- walk this warp's slab: rows tb + 16 warp .. +15, plus two look-ahead rows for the transposed conv
   const int ts = warp * kTileSlab;
-  float ua2[4], ua1[4], ug2[4], ug1[4];
+  float2 ua2[2], ua1[2], ug2[2], ug1[2];
   {
     const uint2 p2 = *reinterpret_cast<const uint2*>(su + ts * 512 + lane * 8);
     const uint2 q2 = *reinterpret_cast<const uint2*>(su + ts * 512 + 256 + lane * 8);
     const uint2 p1 = *reinterpret_cast<const uint2*>(su + (ts + 1) * 512 + lane * 8);
     const uint2 q1 = *reinterpret_cast<const uint2*>(su + (ts + 1) * 512 + 256 + lane * 8);
-    float2 x;
-    x = unpack_bf16x2(p2.x); ua2[0] = x.x; ua2[1] = x.y; x = unpack_bf16x2(p2.y); ua2[2] = x.x; ua2[3] = x.y;
-    x = unpack_bf16x2(q2.x); ug2[0] = x.x; ug2[1] = x.y; x = unpack_bf16x2(q2.y); ug2[2] = x.x; ug2[3] = x.y;
-    x = unpack_bf16x2(p1.x); ua1[0] = x.x; ua1[1] = x.y; x = unpack_bf16x2(p1.y); ua1[2] = x.x; ua1[3] = x.y;
-    x = unpack_bf16x2(q1.x); ug1[0] = x.x; ug1[1] = x.y; x = unpack_bf16x2(q1.y); ug1[2] = x.x; ug1[3] = x.y;
+    ua2[0] = unpack_bf16x2(p2.x); ua2[1] = unpack_bf16x2(p2.y); ug2[0] = unpack_bf16x2(q2.x); ug2[1] = unpack_bf16x2(q2.y);
+    ua1[0] = unpack_bf16x2(p1.x); ua1[1] = unpack_bf16x2(p1.y); ug1[0] = unpack_bf16x2(q1.x); ug1[1] = unpack_bf16x2(q1.y);
   }
-  float da2[4], da1[4], dg2[4], dg1[4], dwa[4][3], dwg[4][3], dgam[4];
+  const float2 z2 = make_float2(0.f, 0.f);
+  float2 da2[2] = {z2, z2}, da1[2] = {z2, z2}, dg2[2] = {z2, z2}, dg1[2] = {z2, z2};
+  float2 dwa[3][2], dwg[3][2], dgam[2] = {z2, z2};
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    da2[e] = da1[e] = dg2[e] = dg1[e] = 0.f; dgam[e] = 0.f;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { dwa[e][k] = 0.f; dwg[e][k] = 0.f; }
-  }
+  for (int k = 0; k < 3; ++k) { dwa[k][0] = dwa[k][1] = z2; dwg[k][0] = dwg[k][1] = z2; }
   const int kshift = (lane & 1) * 4;
   __nv_bfloat16* du_lane = du + (row_base + tb + ts) * ld + g * 256 + lane * 4;
 #pragma unroll 3
@@ -257,71 +257,72 @@ ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, 
     const int tl = ts + i;                              // row tb + tl
     const bool valid = tb + tl < a.N;
     const bool own = i < kTileSlab;                      // later rows are recomputed only for the conv look-ahead
-    float ua0[4], ug0[4], da0[4], dg0[4];
+    float2 ua0[2], ug0[2], da0[2], dg0[2];
     {
       const uint2 p = *reinterpret_cast<const uint2*>(su + (tl + 2) * 512 + lane * 8);
       const uint2 q = *reinterpret_cast<const uint2*>(su + (tl + 2) * 512 + 256 + lane * 8);
-      float2 x;
-      x = unpack_bf16x2(p.x); ua0[0] = x.x; ua0[1] = x.y; x = unpack_bf16x2(p.y); ua0[2] = x.x; ua0[3] = x.y;
-      x = unpack_bf16x2(q.x); ug0[0] = x.x; ug0[1] = x.y; x = unpack_bf16x2(q.y); ug0[2] = x.x; ug0[3] = x.y;
+      ua0[0] = unpack_bf16x2(p.x); ua0[1] = unpack_bf16x2(p.y); ug0[0] = unpack_bf16x2(q.x); ug0[1] = unpack_bf16x2(q.y);
     }
     if (valid) {
       const uint2 dr = *reinterpret_cast<const uint2*>(sd + tl * 256 + lane * 8);
       const float4 st = sst[tl];
-      float d[4];
-      { float2 x = unpack_bf16x2(dr.x); d[0] = x.x; d[1] = x.y; x = unpack_bf16x2(dr.y); d[2] = x.x; d[3] = x.y; }
+      float2 d[2] = {unpack_bf16x2(dr.x), unpack_bf16x2(dr.y)};
       if (a.drop_p > 0.f) {
         const uint32_t kb = static_cast<uint32_t>(skb[tl * 16 + (lane >> 1)]) >> kshift;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) d[e] = ((kb >> e) & 1u) ? d[e] * keep_scale : 0.f;
+        const float2 k0 = make_float2((kb & 1u) ? keep_scale : 0.f, (kb & 2u) ? keep_scale : 0.f);
+        const float2 k1 = make_float2((kb & 4u) ? keep_scale : 0.f, (kb & 8u) ? keep_scale : 0.f);
+        d[0] = mul2(d[0], k0); d[1] = mul2(d[1], k1);
       }
+      const float2 nmean = splat2(-st.x), rstd = splat2(st.y), nm1 = splat2(-st.z), nm2 = splat2(-st.w);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float ya = wa[e][0] * ua2[e] + wa[e][1] * ua1[e] + wa[e][2] * ua0[e];
-        const float yg = wg[e][0] * ug2[e] + wg[e][1] * ug1[e] + wg[e][2] * ug0[e];
-        float phi, pdf;
-        normal_cdf_pdf(yg, phi, pdf);
-        const float ge = yg * phi;
-        const float hhat = (ge * ya - st.x) * st.y;
-        const float gd = gm[e] * d[e];
-        const float dh = (gm[e] != 0.f) ? st.y * (gd - st.z - hhat * st.w) : 0.f;   // padded channels: gamma == 0
-        da0[e] = dh * ge;
-        dg0[e] = dh * ya * fmaf(yg, pdf, phi);
+      for (int q = 0; q < 2; ++q) {
+        const float2 ya = fma2(wa[0][q], ua2[q], fma2(wa[1][q], ua1[q], mul2(wa[2][q], ua0[q])));
+        const float2 yg = fma2(wg[0][q], ug2[q], fma2(wg[1][q], ug1[q], mul2(wg[2][q], ug0[q])));
+        float2 phi, pdf;
+        normal_cdf_pdf2(yg, phi, pdf);
+        const float2 ge = mul2(yg, phi);
+        const float2 hhat = mul2(fma2(ge, ya, nmean), rstd);
+        // dh = rstd * (gamma d - m1 - hhat m2), forced to 0 on padded channels (gamma == 0)
+        const float2 dh = mul2(mul2(rstd, pm[q]), fma2(hhat, nm2, fma2(gm[q], d[q], nm1)));
+        da0[q] = mul2(dh, ge);
+        dg0[q] = mul2(mul2(dh, ya), fma2(yg, pdf, phi));
         if (own) {
-          dgam[e] += d[e] * hhat;
-          dwa[e][0] += da0[e] * ua2[e]; dwa[e][1] += da0[e] * ua1[e]; dwa[e][2] += da0[e] * ua0[e];
-          dwg[e][0] += dg0[e] * ug2[e]; dwg[e][1] += dg0[e] * ug1[e]; dwg[e][2] += dg0[e] * ug0[e];
+          dgam[q] = fma2(d[q], hhat, dgam[q]);
+          dwa[0][q] = fma2(da0[q], ua2[q], dwa[0][q]); dwa[1][q] = fma2(da0[q], ua1[q], dwa[1][q]); dwa[2][q] = fma2(da0[q], ua0[q], dwa[2][q]);
+          dwg[0][q] = fma2(dg0[q], ug2[q], dwg[0][q]); dwg[1][q] = fma2(dg0[q], ug1[q], dwg[1][q]); dwg[2][q] = fma2(dg0[q], ug0[q], dwg[2][q]);
         }
       }
     } else {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) { da0[e] = 0.f; dg0[e] = 0.f; }
+      da0[0] = da0[1] = z2; dg0[0] = dg0[1] = z2;
     }
     if (i >= 2 && tb + tl - 2 < a.N) {   // du[t-2] = w2 dy[t-2] + w1 dy[t-1] + w0 dy[t]
-      float oa[4], og[4];
+      float2 oa[2], og[2];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        oa[e] = wa[e][2] * da2[e] + wa[e][1] * da1[e] + wa[e][0] * da0[e];
-        og[e] = wg[e][2] * dg2[e] + wg[e][1] * dg1[e] + wg[e][0] * dg0[e];
+      for (int q = 0; q < 2; ++q) {
+        oa[q] = fma2(wa[2][q], da2[q], fma2(wa[1][q], da1[q], mul2(wa[0][q], da0[q])));
+        og[q] = fma2(wg[2][q], dg2[q], fma2(wg[1][q], dg1[q], mul2(wg[0][q], dg0[q])));
       }
       __nv_bfloat16* o = du_lane + static_cast<long>(i - 2) * ld;
-      *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(oa[0], oa[1]), pack_bf16x2(oa[2], oa[3]));
-      *reinterpret_cast<uint2*>(o + 128) = make_uint2(pack_bf16x2(og[0], og[1]), pack_bf16x2(og[2], og[3]));
+      *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(oa[0].x, oa[0].y), pack_bf16x2(oa[1].x, oa[1].y));
+      *reinterpret_cast<uint2*>(o + 128) = make_uint2(pack_bf16x2(og[0].x, og[0].y), pack_bf16x2(og[1].x, og[1].y));
     }
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      ua2[e] = ua1[e]; ua1[e] = ua0[e]; ug2[e] = ug1[e]; ug1[e] = ug0[e];
-      da2[e] = da1[e]; da1[e] = da0[e]; dg2[e] = dg1[e]; dg1[e] = dg0[e];
+    for (int q = 0; q < 2; ++q) {
+      ua2[q] = ua1[q]; ua1[q] = ua0[q]; ug2[q] = ug1[q]; ug1[q] = ug0[q];
+      da2[q] = da1[q]; da1[q] = da0[q]; dg2[q] = dg1[q]; dg1[q] = dg0[q];
     }
   }
   // ---- weight gradients: warps combine in shared memory, one global atomic per (channel, tap) and CTA
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    atomicAdd(&sacc[lane * 4 + e], dgam[e]);
+  for (int q = 0; q < 2; ++q) {
+    atomicAdd(&sacc[lane * 4 + 2 * q], dgam[q].x);
+    atomicAdd(&sacc[lane * 4 + 2 * q + 1], dgam[q].y);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      atomicAdd(&sacc[(1 + k) * 128 + lane * 4 + e], dwa[e][k]);
-      atomicAdd(&sacc[(4 + k) * 128 + lane * 4 + e], dwg[e][k]);
+      atomicAdd(&sacc[(1 + k) * 128 + lane * 4 + 2 * q], dwa[k][q].x);
+      atomicAdd(&sacc[(1 + k) * 128 + lane * 4 + 2 * q + 1], dwa[k][q].y);
+      atomicAdd(&sacc[(4 + k) * 128 + lane * 4 + 2 * q], dwg[k][q].x);
+      atomicAdd(&sacc[(4 + k) * 128 + lane * 4 + 2 * q + 1], dwg[k][q].y);
     }
   }
   __syncthreads();

@@ -111,7 +111,7 @@ gemm_ffn_up_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (!first) asm volatile("bar.sync 2, 256;" ::: "memory");   // everyone is done reading the previous u tile
       first = false;
       // conv taps of this lane's 4 value + 4 gate channels (phase 2 mapping), fetched under the wait for the MMAs
-      float wv[4][3], wg[4][3];
+      float2 wv[3][2], wg[3][2];                    // taps [k][channel pair]
       {
         const float4* wp = reinterpret_cast<const float4*>(conv_w + static_cast<long>(n_blk * kFuBN + lane * 4) * 3);
         const float4* gp = reinterpret_cast<const float4*>(conv_w + static_cast<long>(n_blk * kFuBN + 128 + lane * 4) * 3);
@@ -120,9 +120,12 @@ gemm_ffn_up_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const float fa[12] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
         const float fb[12] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
+        for (int k = 0; k < 3; ++k)
 #pragma unroll
-          for (int k = 0; k < 3; ++k) { wv[e][k] = fa[e * 3 + k]; wg[e][k] = fb[e * 3 + k]; }
+          for (int q = 0; q < 2; ++q) {
+            wv[k][q] = make_float2(fa[(2 * q) * 3 + k], fa[(2 * q + 1) * 3 + k]);
+            wg[k][q] = make_float2(fb[(2 * q) * 3 + k], fb[(2 * q + 1) * 3 + k]);
+          }
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -159,21 +162,18 @@ gemm_ffn_up_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int nrows = min(min(16, kFuBM - t0), static_cast<int>(min(static_cast<long>(16), M - grow0)));
         int pos = static_cast<int>(grow0 % Nseq);
         const uint8_t* rp = usm + t0 * kFuUPitch;
-        float xv1[4], xg1[4], xv2[4], xg2[4];
+        float2 xv1[2], xg1[2], xv2[2], xg2[2];        // fp32x2 pairs: channels (0,1) and (2,3) of this lane
         {
           const uint2 a = *reinterpret_cast<const uint2*>(rp - kFuUPitch + lane * 8);
           const uint2 g = *reinterpret_cast<const uint2*>(rp - kFuUPitch + 256 + lane * 8);
-          const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y);
-          xv1[0] = a0.x; xv1[1] = a0.y; xv1[2] = a1.x; xv1[3] = a1.y;
-          xg1[0] = g0.x; xg1[1] = g0.y; xg1[2] = g1.x; xg1[3] = g1.y;
+          xv1[0] = unpack_bf16x2(a.x); xv1[1] = unpack_bf16x2(a.y); xg1[0] = unpack_bf16x2(g.x); xg1[1] = unpack_bf16x2(g.y);
         }
         {
           const uint2 a = *reinterpret_cast<const uint2*>(rp - 2 * kFuUPitch + lane * 8);
           const uint2 g = *reinterpret_cast<const uint2*>(rp - 2 * kFuUPitch + 256 + lane * 8);
-          const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y);
-          xv2[0] = a0.x; xv2[1] = a0.y; xv2[2] = a1.x; xv2[3] = a1.y;
-          xg2[0] = g0.x; xg2[1] = g0.y; xg2[2] = g1.x; xg2[3] = g1.y;
+          xv2[0] = unpack_bf16x2(a.x); xv2[1] = unpack_bf16x2(a.y); xg2[0] = unpack_bf16x2(g.x); xg2[1] = unpack_bf16x2(g.y);
         }
+        if (pos == 1) { xv2[0] = xv2[1] = xg2[0] = xg2[1] = make_float2(0.f, 0.f); }   // row t-2 belongs to the previous sequence
         float st[32];
         __nv_bfloat16* ug = u_out + grow0 * (2L * Fp) + n_blk * kFuBN + lane * 8;
         __nv_bfloat16* hg = h_out + grow0 * static_cast<long>(Fp) + n_blk * 128 + lane * 4;
@@ -185,21 +185,25 @@ gemm_ffn_up_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             *reinterpret_cast<uint4*>(ug + static_cast<long>(r) * (2L * Fp)) = *reinterpret_cast<const uint4*>(rr + lane * 16);
             const uint2 a = *reinterpret_cast<const uint2*>(rr + lane * 8);
             const uint2 g = *reinterpret_cast<const uint2*>(rr + 256 + lane * 8);
-            const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y);
-            const float xv0[4] = {a0.x, a0.y, a1.x, a1.y}, xg0[4] = {g0.x, g0.y, g1.x, g1.y};
-            const float k1 = pos >= 1 ? 1.f : 0.f, k2 = pos >= 2 ? 1.f : 0.f;   // no history across sequence starts
-            float h[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float yv = wv[e][2] * xv0[e] + k1 * (wv[e][1] * xv1[e]) + k2 * (wv[e][0] * xv2[e]);
-              const float yg = wg[e][2] * xg0[e] + k1 * (wg[e][1] * xg1[e]) + k2 * (wg[e][0] * xg2[e]);
-              h[e] = gelu_erf(yg) * yv;
-              s1 += h[e];
-              s2 += h[e] * h[e];
-              xv2[e] = xv1[e]; xv1[e] = xv0[e];
-              xg2[e] = xg1[e]; xg1[e] = xg0[e];
+            const float2 xv0[2] = {unpack_bf16x2(a.x), unpack_bf16x2(a.y)}, xg0[2] = {unpack_bf16x2(g.x), unpack_bf16x2(g.y)};
+            if (pos == 0) {   // sequence start: no history (the zeros then slide into the t-2 slot for the next row)
+              const float2 z = make_float2(0.f, 0.f);
+              xv1[0] = xv1[1] = xg1[0] = xg1[1] = z;
+              xv2[0] = xv2[1] = xg2[0] = xg2[1] = z;
             }
-            *reinterpret_cast<uint2*>(hg + static_cast<long>(r) * Fp) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+            float2 h[2], sq = make_float2(0.f, 0.f), sm = sq;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const float2 yv = fma2(wv[0][q], xv2[q], fma2(wv[1][q], xv1[q], mul2(wv[2][q], xv0[q])));
+              const float2 yg = fma2(wg[0][q], xg2[q], fma2(wg[1][q], xg1[q], mul2(wg[2][q], xg0[q])));
+              h[q] = mul2(gelu_erf2(yg), yv);
+              sm = add2(sm, h[q]);
+              sq = fma2(h[q], h[q], sq);
+              xv2[q] = xv1[q]; xv1[q] = xv0[q];
+              xg2[q] = xg1[q]; xg1[q] = xg0[q];
+            }
+            s1 = sm.x + sm.y; s2 = sq.x + sq.y;
+            *reinterpret_cast<uint2*>(hg + static_cast<long>(r) * Fp) = make_uint2(pack_bf16x2(h[0].x, h[0].y), pack_bf16x2(h[1].x, h[1].y));
             if (++pos == Nseq) pos = 0;
           }
           st[2 * r] = s1;

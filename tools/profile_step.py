@@ -21,10 +21,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ncu", action="store_true")
     ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--depth", type=int, default=None, help="override the layer count (1 keeps an ncu --set full capture short)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "step_breakdown.json"))
     args = ap.parse_args()
     torch.manual_seed(0)
-    model = O.create_coarse_transformer(**bench.CFG).cuda()
+    cfg = dict(bench.CFG)
+    if args.depth is not None:
+        cfg["depth"] = args.depth
+    model = O.create_coarse_transformer(**cfg).cuda()
     tr = O.HotPathTrainer(model, cross_entropy_loss_weights=bench.TRAIN["ce_weights"], lr=3e-4, lr_warmup=6000, wd=0.01, use_cuda_graph=False)
     gen = torch.Generator().manual_seed(1234)
     batch = [t.cuda() for t in bench.synth_batch(args.batch, gen)]

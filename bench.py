@@ -12,6 +12,7 @@ Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -267,12 +268,14 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, finish=None):
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
             fn(i)
+        if finish is not None:
+            finish()
         e1.record()
         sync_all()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -281,7 +284,19 @@ def run_b200(args):
         return float(ms) / steps
 
     step_dev = lambda i: tr.train_step([pool_dev[i % len(pool_dev)]])
-    step_e2e = lambda i: float(tr.train_step([pool_host[i % len(pool_host)]]))      # H2D of the batch + D2H of the loss
+    # end to end through the public trainer API: every step copies its batch from pinned host memory and its loss back
+    # to the host; the loss of step i is read on the host while step i+1 runs (one-step logging lag), the last one
+    # before the timed region closes
+    pending, host_losses = [], []
+
+    def step_e2e(i):
+        pending.append(tr.train_step_async([pool_host[i % len(pool_host)]]))
+        if len(pending) > 1:
+            host_losses.append(pending.pop(0).value())
+
+    def drain_e2e():
+        while pending:
+            host_losses.append(pending.pop(0).value())
 
     # first step: eager launches, counted (the CUDA graph captured two steps later replays exactly these kernels)
     launches["n"] = 0
@@ -295,7 +310,10 @@ def run_b200(args):
     ms_step = timed(step_dev, args.steps)
     for i in range(2):
         step_e2e(i)
-    ms_e2e = timed(step_e2e, args.steps)
+    drain_e2e()
+    host_losses.clear()
+    ms_e2e = timed(step_e2e, args.steps, finish=drain_e2e)
+    assert len(host_losses) == args.steps and all(math.isfinite(v) for v in host_losses), "e2e: every step's loss must reach the host"
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- instrumented steps: GEMM family (the dominant kernel) with one CUDA-event pair per launch
@@ -316,6 +334,16 @@ def run_b200(args):
         fwd_fn(i)
     ms_fwd = timed(fwd_fn, args.steps)
 
+    # order check: the device loop again, now after the e2e and instrumented loops (same K), to expose any
+    # power-cap / clock drift between the first and the later timed regions
+    for i in range(2):
+        step_dev(i)
+    ms_step_again = timed(step_dev, args.steps)
+    gemm_traffic = {}
+    try:   # DRAM bytes of the GEMM family from the committed ncu --set full capture (tools/ncu_summarize.py)
+        gemm_traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_gemm_traffic.json")))
+    except (OSError, ValueError):
+        pass
     fl = flops_per_step(B)
     peaks = load_peaks()
     tok = world * B * SEQ_N
@@ -327,18 +355,20 @@ def run_b200(args):
         ach = g_fl / (g_ms * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": tok / (ms_step * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "ms_per_step_recheck_after_e2e": ms_step_again, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "musiclm_small coarse-stage training step (BASELINE.json configs[1]): d=1024 L=6 h=8 conv-FFN F=2730, "
                                    "N=1024 (clap 12 + semantic 197 + coarse 270x3), dropout 0.1 + forgetful mask 0.15, AdamW + clip 0.5",
                        "global_batch": world * B, "per_gpu_batch": B, "seq_len": SEQ_N, "parallelism": f"dp{world}",
                        "l2": "no explicit flush: one step touches > 3 GB of activations/weights, far above the 126 MB L2"},
             "e2e": {"value": tok / (ms_e2e * 1e-3), "unit": "tokens/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": 4},
+                    "d2h_bytes_per_step": 4,
+                    "api": "HotPathTrainer.train_step_async: batch copied from pinned host memory every step, loss copied "
+                           "to pinned host memory every step and read on the host one step later (last one inside the timed region)"},
             "gpu_launches": n_launch * args.steps, "gpu_launches_per_step": n_launch,
             "launch_mode": "step replayed from two CUDA graphs (fwd+bwd | clip+AdamW+pack), NCCL all-reduce eager between them" if tr.use_cuda_graph else "eager launches",
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel + gemm_ffn_up_kernel (tcgen05; all operand-major variants; FFN-up time includes its fused conv+GEGLU epilogue)", "achieved": ach,
-                         "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": ach / peaks["sustained"], "traffic": None,
+                         "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": ach / peaks["sustained"], "traffic": gemm_traffic.get("bytes_per_launch"), "traffic_unit": "bytes per launch (family average)", "traffic_source": gemm_traffic.get("source"),
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']})",
                          "launches_per_step": n_gemm, "gemm_ms_per_step": g_ms / args.steps,
                          "gemm_share_of_step": (g_ms / args.steps) / ms_instr, "ms_per_step_instrumented": ms_instr},

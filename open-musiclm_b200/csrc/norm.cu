@@ -138,51 +138,53 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     const uint8_t* sb = wbuf + stage * kStage;
-    float4 hh[NCHUNK], gg[NCHUNK];
-    float s1 = 0.f, s2 = 0.f;
+    // element-wise math on fp32x2 pairs (FFMA2): with 8 warps per SM this kernel is bound by instruction issue
+    float2 hA[NCHUNK], hB[NCHUNK], gA[NCHUNK], gB[NCHUNK];
+    float2 s1v = make_float2(0.f, 0.f), s2v = s1v;
+    const float2 rs2 = splat2(st.y), nmr = splat2(-st.x * st.y);          // xhat = x * rstd - mean * rstd
 #pragma unroll
     for (int c = 0; c < NCHUNK; ++c) {
       const int col = (c * 32 + lane) * 4;
-      hh[c] = make_float4(0.f, 0.f, 0.f, 0.f); gg[c] = hh[c];
+      hA[c] = hB[c] = gA[c] = gB[c] = make_float2(0.f, 0.f);
       if (col < D && d_cur >= 0) {
         const float4 xv = *reinterpret_cast<const float4*>(sb + col * 4);
         const uint2 dv = *reinterpret_cast<const uint2*>(sb + kRow * 8 + col * 2);
-        const float2 d01 = unpack_bf16x2(dv.x), d23 = unpack_bf16x2(dv.y);
-        const float h0 = (xv.x - st.x) * st.y, h1 = (xv.y - st.x) * st.y, h2 = (xv.z - st.x) * st.y, h3 = (xv.w - st.x) * st.y;
-        dg[c].x += d01.x * h0; dg[c].y += d01.y * h1; dg[c].z += d23.x * h2; dg[c].w += d23.y * h3;
-        const float g0 = d01.x * gm[c].x, g1 = d01.y * gm[c].y, g2 = d23.x * gm[c].z, g3 = d23.y * gm[c].w;
-        s1 += g0 + g1 + g2 + g3;
-        s2 += g0 * h0 + g1 * h1 + g2 * h2 + g3 * h3;
-        hh[c] = make_float4(h0, h1, h2, h3); gg[c] = make_float4(g0, g1, g2, g3);
+        const float2 dA = unpack_bf16x2(dv.x), dB = unpack_bf16x2(dv.y);
+        hA[c] = fma2(make_float2(xv.x, xv.y), rs2, nmr);
+        hB[c] = fma2(make_float2(xv.z, xv.w), rs2, nmr);
+        const float2 a = fma2(dA, hA[c], make_float2(dg[c].x, dg[c].y)), b2 = fma2(dB, hB[c], make_float2(dg[c].z, dg[c].w));
+        dg[c] = make_float4(a.x, a.y, b2.x, b2.y);
+        gA[c] = mul2(dA, make_float2(gm[c].x, gm[c].y));
+        gB[c] = mul2(dB, make_float2(gm[c].z, gm[c].w));
+        s1v = add2(s1v, add2(gA[c], gB[c]));
+        s2v = fma2(gA[c], hA[c], fma2(gB[c], hB[c], s2v));
       }
     }
-    s1 = warp_sum(s1) / D;
-    s2 = warp_sum(s2) / D;
+    const float s1 = warp_sum(s1v.x + s1v.y) / D;
+    const float s2 = warp_sum(s2v.x + s2v.y) / D;
+    const float2 ns1r = splat2(-s1 * st.y), ns2r = splat2(-s2 * st.y);   // dx = g*rstd - s1*rstd - xhat*s2*rstd
 #pragma unroll
     for (int c = 0; c < NCHUNK; ++c) {
       const int col = (c * 32 + lane) * 4;
       if (col < D) {
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        float2 oA = make_float2(0.f, 0.f), oB = oA;
         if (d_cur >= 0) {
-          o.x = st.y * (gg[c].x - s1 - hh[c].x * s2);
-          o.y = st.y * (gg[c].y - s1 - hh[c].y * s2);
-          o.z = st.y * (gg[c].z - s1 - hh[c].z * s2);
-          o.w = st.y * (gg[c].w - s1 - hh[c].w * s2);
+          oA = fma2(hA[c], ns2r, fma2(gA[c], rs2, ns1r));
+          oB = fma2(hB[c], ns2r, fma2(gB[c], rs2, ns1r));
         }
         if (dres != nullptr) {
           const float4 r = *reinterpret_cast<const float4*>(sb + kRow * 4 + col * 4);
-          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+          oA = add2(oA, make_float2(r.x, r.y)); oB = add2(oB, make_float2(r.z, r.w));
         }
         if (draw != nullptr) {
           const uint2 rv = *reinterpret_cast<const uint2*>(sb + kRow * 10 + col * 2);
-          const float2 r01 = unpack_bf16x2(rv.x), r23 = unpack_bf16x2(rv.y);
-          o.x += r01.x; o.y += r01.y; o.z += r23.x; o.w += r23.y;
+          oA = add2(oA, unpack_bf16x2(rv.x)); oB = add2(oB, unpack_bf16x2(rv.y));
         }
-        *reinterpret_cast<float4*>(dx + static_cast<long long>(row) * D + col) = o;
+        *reinterpret_cast<float4*>(dx + static_cast<long long>(row) * D + col) = make_float4(oA.x, oA.y, oB.x, oB.y);
         if (dx_bf16 != nullptr) {
           uint2 ob;
-          ob.x = pack_bf16x2(o.x, o.y);
-          ob.y = pack_bf16x2(o.z, o.w);
+          ob.x = pack_bf16x2(oA.x, oA.y);
+          ob.y = pack_bf16x2(oB.x, oB.y);
           *reinterpret_cast<uint2*>(dx_bf16 + static_cast<long long>(row) * D + col) = ob;
         }
       }

@@ -24,6 +24,17 @@ from .dist_utils import allreduce_sum_, grad_prescale, rank_seed, world_info
 from .model import TokenConditionedTransformer
 
 
+class LossHandle:
+    """Host-side view of one step's loss (see HotPathTrainer.train_step_async)."""
+
+    def __init__(self, host_scalar: torch.Tensor, event: "torch.cuda.Event"):
+        self._host, self._event = host_scalar, event
+
+    def value(self) -> float:
+        self._event.synchronize()
+        return float(self._host)
+
+
 class HotPathTrainer:
     def __init__(self, transformer: TokenConditionedTransformer, *, cross_entropy_loss_weights: Optional[List[float]] = None,
                  lr=3e-4, lr_warmup=0, wd=0., max_grad_norm=0.5, grad_accum_every=1, mask_prob=0.15,
@@ -51,6 +62,7 @@ class HotPathTrainer:
         self.use_cuda_graph = use_cuda_graph
         self._graphs = {}
         self.loss_out = torch.zeros((), device=eng.dev)
+        self._loss_ring = None
         eng.arena_g.zero_()
 
     # -------------------------------------------------------------------------------------------
@@ -186,6 +198,19 @@ class HotPathTrainer:
                 gb.replay()
         self.steps += 1
         return self.loss_out
+
+    def train_step_async(self, micro_batches: Sequence[Sequence[torch.Tensor]]) -> "LossHandle":
+        """train_step() plus an asynchronous device->host copy of the step's loss into pinned memory.  The returned
+        handle's value() blocks only on that copy, so a training loop can log step i's loss while step i+1 is already
+        running on the GPU (the usual one-step logging lag) instead of draining the stream after every step."""
+        loss = self.train_step(micro_batches)
+        if self._loss_ring is None:
+            self._loss_ring = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(4)]
+        slot = self._loss_ring[self.steps % len(self._loss_ring)]
+        slot.copy_(loss, non_blocking=True)       # stream-ordered before the next step overwrites loss_out
+        ev = torch.cuda.Event()
+        ev.record()
+        return LossHandle(slot, ev)
 
     @torch.no_grad()
     def eval_loss(self, token_ids: Sequence[torch.Tensor]):

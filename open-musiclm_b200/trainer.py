@@ -55,7 +55,9 @@ class HotPathTrainer:
         eng.seed.fill_(rank_seed(seed, self.rank))     # per-rank random streams (dropout / forgetful mask)
         eng.adam_m = torch.zeros_like(eng.arena_p)
         eng.adam_v = torch.zeros_like(eng.arena_p)
-        self.hyper_host = torch.zeros(9, dtype=torch.float32).pin_memory()
+        # PAGEABLE on purpose: cudaMemcpyAsync stages a pageable source before it returns, so the host may already write
+        # the next step's values while earlier steps are still queued (a pinned buffer would be read late -> wrong step)
+        self.hyper_host = torch.zeros(9, dtype=torch.float32)
         self.hyper = torch.zeros(9, dtype=torch.float32, device=eng.dev)
         self.loss_buf = torch.zeros(grad_accum_every, device=eng.dev)
         self._mask_draws = 0

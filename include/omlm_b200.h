@@ -123,8 +123,8 @@ int omlm_attn_bwd_tc(const void* qn, const void* kvn, const void* d_o, const voi
  * Interleaved GEGLU layout: Fp = F rounded up to 128; u / W1 rows / conv taps are ordered in groups of 128 channels as
  * [128 value | 128 gate]; h / hn / gamma / W2 columns are in natural channel order (zero padded to Fp).
  * FFN up-projection GEMM (tcgen05) with the causal depthwise conv (k=3), GEGLU (exact erf) and the LayerNorm row
- * statistics fused into its epilogue:  u bf16 [M, 2Fp], h bf16 [M, Fp], rowsum fp32 [M, 2] += (sum h, sum h^2)
- * (rowsum must be zero on entry).  M = B * Nseq rows, sequences of Nseq consecutive rows. */
+ * statistics fused into its epilogue:  u bf16 [M, 2Fp], h bf16 [M, Fp], rowsum fp32 [M, Fp/128, 2] = per-128-channel
+ * partial (sum h, sum h^2), plain stores (no zeroing needed; summed in a fixed order by omlm_ffn_norm_fwd).  M = B * Nseq rows, sequences of Nseq consecutive rows. */
 int omlm_gemm_ffn_up(const void* xn, const void* w1_packed, const float* conv_w_packed, void* u_out, void* h_out,
                      float* rowsum, int M, int Nseq, int K, int Fp, int max_ctas, void* stream);
 /* hn = dropout(LayerNorm_F(h)) from the fused statistics; stats fp32 [M, 2] = (mean, rstd) for the backward pass.

@@ -72,7 +72,11 @@ ffn_norm_fwd_kernel(const __nv_bfloat16* __restrict__ h, const float2* __restric
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long row = static_cast<long>(blockIdx.x) * 8 + warp;
   if (row >= M) return;
-  const float2 rsum = rowsum[row];
+  // per-tile partial sums from the FFN-up epilogue, [row][Fp/128] float2: fixed-order (butterfly) reduction
+  const int n_tiles = Fp >> 7;
+  float2 rsum = make_float2(0.f, 0.f);
+  for (int t = lane; t < n_tiles; t += 32) { const float2 p = rowsum[row * n_tiles + t]; rsum.x += p.x; rsum.y += p.y; }
+  rsum.x = warp_sum(rsum.x); rsum.y = warp_sum(rsum.y);
   const float mean = rsum.x / F;
   const float var = fmaxf(rsum.y / F - mean * mean, 0.f);
   const float rstd = rsqrtf(var + 1e-5f);

@@ -5,7 +5,7 @@
 //   u = xn @ W1^T                  [M, 2Fp]  (bf16, kept for the backward pass)      transformer.py:144
 //   y[t] = w0 u[t-2] + w1 u[t-1] + w2 u[t]   per channel, zero history at sequence start   transformer.py:122-131
 //   h = gelu_erf(y_gate) * y_value  [M, Fp]  (bf16)                                         transformer.py:134-137
-//   rowsum[m] += (sum_c h, sum_c h^2)   -> LayerNorm(F) statistics for omlm_ffn_norm_fwd    transformer.py:147
+//   rowsum[m][n tile] = (sum_c h, sum_c h^2) over the tile's 128 channels -> LN(F) statistics  transformer.py:147
 //
 // Tiling: 128 x 256 x 64, W1 rows interleaved so that one 256-column tile = [128 value | 128 gate] columns of the same
 // 128 channels.  The conv needs rows t-1, t-2, so M tiles overlap by two rows (tile i covers rows 126 i - 2 ..
@@ -220,7 +220,10 @@ gemm_ffn_up_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             st[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
           }
         }
-        if ((lane >> 1) < nrows) atomicAdd(rowsum + 2 * grow0 + lane, st[0]);
+        // per-tile partial sums, one slot per (row, n tile): omlm_ffn_norm_fwd adds the n_tiles partials in a fixed
+        // order, so the forward pass stays bit-reproducible (fp32 atomics would make the LayerNorm statistics, and
+        // after six layers of bf16 rounding every logit, depend on CTA timing)
+        if ((lane >> 1) < nrows) rowsum[(grow0 + (lane >> 1)) * (2L * n_tiles) + 2 * n_blk + (lane & 1)] = st[0];
       }
     }
   }

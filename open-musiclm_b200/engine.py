@@ -213,7 +213,7 @@ class Engine:
             xn2=[E(M, d) for _ in range(nl)], st_f=[E(M, 2, dt=f32) for _ in range(nl)],
             u=[E(M, 2 * Fp) for _ in range(nl)], hn=[E(M, Fp) for _ in range(nl)], st_i=[E(M, 2, dt=f32) for _ in range(nl)],
             keep=[E(M, Fp // 8, dt=torch.uint8) for _ in range(nl)],   # FFN dropout keep mask, 1 bit per element
-            xf=E(max(pl.rows_total, 1), d), st_o=E(M, 2, dt=f32), h=E(M, Fp), rowsum=E(M, 2, dt=f32),
+            xf=E(max(pl.rows_total, 1), d), st_o=E(M, 2, dt=f32), h=E(M, Fp), rowsum=E(M, Fp // 128, 2, dt=f32),
             logits=[E(max(pl.B * c, 1), self.Cp[s], dt=f32) for (s, qi, c, b0) in pl.groups],
             # rel-pos MLP
             rp_in=E(pl.N, 1, dt=f32), rp_z=[E(pl.N, self.Hr, dt=f32) for _ in range(3)],
@@ -268,9 +268,8 @@ class Engine:
             lib.split3_bf16(ws["rp_a"][j - 1], ws["rp_a3"][j - 1])
             lib.gemm(ws["rp_a3"][j - 1], self.pk_rp[j - 1], ws["rp_z"][j], block_n=128)
             lib.bias_silu(ws["rp_z"][j], pv[f"{pre}{j}.0.bias"], ws["rp_a"][j])
-        ws["table"].zero_()      # split-K accumulate: 16 CTAs with a 512-long reduction each would leave the GPU idle
-        lib.sgemm_small(ws["rp_a"][2], (Hr, 1), pv[pre + "3.weight"], (1, Hr), ws["table"], (1, N), N, h, Hr, bias=pv[pre + "3.bias"],
-                        accumulate=True)
+        # no split-K here: atomics would make the table, and through bf16 rounding every logit, depend on CTA timing
+        lib.sgemm_small(ws["rp_a"][2], (Hr, 1), pv[pre + "3.weight"], (1, Hr), ws["table"], (1, N), N, h, Hr, bias=pv[pre + "3.bias"])
 
     def forward_core(self, pl: _Plan, ws, src_row, key_mask, train: bool, groups_wanted=None, drop: bool = False):
         """Runs embeddings -> depth x (attention, conv-FFN) -> final LN -> logit heads.  Activations stay in `ws`."""
@@ -292,7 +291,6 @@ class Engine:
             lib.attn_fwd_tc(ws["qn"][i], ws["kvn"][i], ws["table"], key_mask, ws["o"][i], ws["lse"][i], B, N, h)
             lib.gemm(ws["o"][i], pk["wo"], xm, addend=xa, block_n=self._bn_for(M, d, HD))
             lib.layernorm_fwd(xm, pv[p + "2.0.gamma"], ws["xn2"][i], None, ws["st_f"][i])
-            ws["rowsum"].zero_()
             lib.gemm_ffn_up(ws["xn2"][i], pk["w1"], pk["conv"], ws["u"][i], ws["h"], ws["rowsum"], N, Fp)   # conv + GEGLU in the epilogue
             lib.ffn_norm_fwd(ws["h"], ws["rowsum"], pk["gin"], ws["hn"][i], ws["st_i"][i], F, Fp, drop_p, self.seed, l,
                              keep_bits=ws["keep"][i] if drop_p > 0 else None)

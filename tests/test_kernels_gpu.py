@@ -259,7 +259,7 @@ def test_ffn_up_fused_and_mid_bwd(lib, B, N, d, F_, drop_p):
     assert torch.equal(w1p[cols], W1.bfloat16()) and torch.equal(cwp[cols], cw)
     u = torch.full((M, 2 * Fp), float("nan"), device=DEV, dtype=torch.bfloat16)
     h = torch.full((M, Fp), float("nan"), device=DEV, dtype=torch.bfloat16)
-    rowsum = torch.zeros(M, 2, device=DEV)
+    rowsum = torch.full((M, Fp // 128, 2), float("nan"), device=DEV)
     lib.gemm_ffn_up(xn, w1p, cwp, u, h, rowsum, N, Fp)
     hn = torch.empty(M, Fp, device=DEV, dtype=torch.bfloat16); stats = torch.empty(M, 2, device=DEV)
     seed = torch.tensor([99], dtype=torch.int64, device=DEV)
@@ -276,7 +276,7 @@ def test_ffn_up_fused_and_mid_bwd(lib, B, N, d, F_, drop_p):
     hmid = F.gelu(y[..., F_:]) * y[..., :F_]
     assert rel(h[:, :F_], hmid.detach().reshape(M, F_)) < 5e-3
     assert float(h[:, F_:].abs().max()) == 0
-    assert rel(rowsum[:, 0], hmid.detach().reshape(M, F_).sum(1)) < 2e-3
+    assert rel(rowsum.sum(1)[:, 0], hmid.detach().reshape(M, F_).sum(1)) < 2e-3
     ref = F.layer_norm(hmid, (F_,), gr, None, 1e-5).reshape(M, F_)
     if drop_p > 0:
         keep = ((kbits[:, :, None] >> torch.arange(8, device=DEV, dtype=torch.uint8)) & 1).bool().reshape(M, Fp)[:, :F_]

@@ -260,3 +260,32 @@ def test_cfg2_full_size_properties():
         tr.train_step([batch])
     l1 = float(tr.eval_loss(batch))
     assert l1 < l0, (l0, l1)
+
+
+def test_forward_is_bit_reproducible():
+    """Two forward passes over the same tokens give bit-identical activations and logits: nothing on the forward path
+    uses floating-point atomics (bf16 rounding would amplify a 1e-7 reordering difference to ~5e-3 over six layers,
+    which is what made an earlier version's logits wander from run to run)."""
+    import open_musiclm_b200 as O
+    torch.manual_seed(0)
+    m = O.create_coarse_transformer(dim=1024, depth=3, heads=8, num_coarse_quantizers=3, attn_dropout=0.0, ff_dropout=0.1).cuda().eval()
+    tr = O.HotPathTrainer(m, cross_entropy_loss_weights=[0.0, 0.0, 1.0], use_cuda_graph=False)
+    g = torch.Generator().manual_seed(1234)
+    toks = [torch.randint(0, 1024, (4, 12), generator=g).cuda(), torch.randint(0, 1024, (4, 197), generator=g).cuda(),
+            torch.randint(0, 1024, (4, 270, 3), generator=g).cuda()]
+
+    def snap():
+        tr._micro_batch(toks, False, 0, True)          # training-layout workspaces: one buffer per layer
+        torch.cuda.synchronize()
+        ws = next(iter(tr.eng._ws.values()))
+        out = {}
+        for k in ("table", "x", "o", "u", "hn", "logits"):
+            v = ws[k]
+            out[k] = [t.clone() for t in v] if isinstance(v, list) else [v.clone()]
+        tr.eng.arena_g.zero_()
+        return out
+
+    a, b = snap(), snap()
+    for k in a:
+        for i, (p, q) in enumerate(zip(a[k], b[k])):
+            assert torch.equal(p, q), (k, i, float((p.double() - q.double()).abs().max()))

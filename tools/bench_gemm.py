@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.ins
 import torch
 from open_musiclm_b200 import lib
 from open_musiclm_b200.engine import Engine as E
-M, d, HD, Fp, F = 16384, 1024, 512, 2752, 2730
+M, d, HD, Fp, F = 16384, 1024, 512, 2816, 2730
 dev = "cuda"
 def t(fn, n=10):
     for _ in range(3): fn()

@@ -2,7 +2,8 @@
 //
 //   warp 0      : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1      : tcgen05.mma issuer (one elected lane), accumulators in TMEM, double-buffered
-//   warps 2..5  : epilogue (tcgen05.ld TMEM -> registers -> fused epilogue -> global)
+//   warps 2..9  : epilogue (tcgen05.ld TMEM -> registers -> fused epilogue -> global); two warps per TMEM lane
+//                 quarter (= per SM sub-partition), each draining one half of the tile's columns
 //
 // Operand majors are template parameters so that one kernel serves the forward projections
 // (A K-major, B K-major: nn.Linear weights are [out,in]), the data-gradient GEMMs (B MN-major: the
@@ -19,7 +20,7 @@ namespace omlm {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;
 constexpr int kSmemBudget = 196608;  // ring bytes
 
 struct EpiParams {
@@ -80,7 +81,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull_bar[i], 1);
-        mbar_init(&tempty_bar[i], 4);
+        mbar_init(&tempty_bar[i], 8);
       }
       fence_barrier_init();
     }
@@ -166,6 +167,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // ------------------------------------------------------------------ epilogue warps
     const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    const int c_lo = ((warp - 2) >> 2) * (BN / 64), c_hi = c_lo + BN / 64;   // this warp's half of the 32-column chunks
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
@@ -189,17 +191,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       float4 nxt[8];
       auto prefetch = [&](int c) {
         const int col0 = n_blk * BN + c * 32;
-        if (pf && c < BN / 32 && col0 + 32 <= ep.n_valid) {
+        if (pf && c < c_hi && col0 + 32 <= ep.n_valid) {
           const float4* ap = reinterpret_cast<const float4*>(ep.addend + static_cast<long>(row) * ep.ldadd + col0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) nxt[j] = ap[j];
         }
       };
-      prefetch(0);
+      prefetch(c_lo);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = c_lo; c < c_hi; ++c) {
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
         float4 cur[8];

@@ -1,3 +1,4 @@
+"""Diagnostic: causality of the full-size coarse forward (perturb late tokens, report which logit positions move)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch

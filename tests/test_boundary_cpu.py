@@ -70,3 +70,23 @@ def test_unsupported_configs_fail_loudly():
                dict(non_causal_prefix_size=4), dict(attn_dropout=0.1), dict(use_memory_efficient_attention=True)]:
         with pytest.raises(NotImplementedError):
             O.create_semantic_transformer(dim=64, depth=1, heads=1, **kw)
+
+
+def test_pack_job_struct_matches_header():
+    """lib._PackJob (ctypes) mirrors `omlm_pack_job` of include/omlm_b200.h field for field: the job table is built on
+    the host and read by omlm_pack_multi on the device."""
+    import ctypes
+    import re
+    from open_musiclm_b200 import lib
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "omlm_b200.h")).read()
+    body = re.search(r"typedef struct \{(.*?)\} omlm_pack_job;", hdr, re.S).group(1)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        for part in decl.split(","):
+            names.append(re.sub(r"[\s\*]", " ", part).split()[-1])
+    assert names == [f[0] for f in lib._PackJob._fields_]
+    assert ctypes.sizeof(lib._PackJob) == 2 * 8 + 3 * 8 + 8 * 4
+    assert lib._PackJob.unit_start.offset == 32 and lib._PackJob.rows_valid.offset == 40

@@ -204,7 +204,8 @@ class HotPathTrainer:
     def train_step_async(self, micro_batches: Sequence[Sequence[torch.Tensor]]) -> "LossHandle":
         """train_step() plus an asynchronous device->host copy of the step's loss into pinned memory.  The returned
         handle's value() blocks only on that copy, so a training loop can log step i's loss while step i+1 is already
-        running on the GPU (the usual one-step logging lag) instead of draining the stream after every step."""
+        running on the GPU (the usual one-step logging lag) instead of draining the stream after every step.
+        The pinned slots form a ring of 4: read a handle before 4 further steps have been issued."""
         loss = self.train_step(micro_batches)
         if self._loss_ring is None:
             self._loss_ring = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(4)]

@@ -23,29 +23,60 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CFG = dict(dim=1024, depth=6, heads=8, num_coarse_quantizers=3, attn_dropout=0.0, ff_dropout=0.1, grad_shrink_alpha=0.1)
-SHAPES = dict(clap=12, semantic=197, coarse=(270, 3))          # N = 1 + 13 + 1 + 198 + 1 + 810 = 1024
 TRAIN = dict(lr=3e-4, lr_warmup=6000, wd=0.01, max_grad_norm=0.5, ce_weights=[0.0, 0.0, 1.0])   # configs/training/*.json
-SEQ_N = 1024
+COMMON = dict(dim=1024, attn_dropout=0.0, ff_dropout=0.1, grad_shrink_alpha=0.1)
+# BASELINE.json configs[1..3]: token shapes per sequence, per-GPU batch, N = positions fed to the transformer
+WORKLOADS = {
+    "cfg2": dict(stage="coarse", model=dict(depth=6, heads=8, num_coarse_quantizers=3), shapes=[(12,), (197,), (270, 3)], batch=16, N=1024, n_pred=811,
+                 name="musiclm_small coarse-stage training step (BASELINE.json configs[1]): d=1024 L=6 h=8 conv-FFN F=2730, "
+                      "N=1024 (clap 12 + semantic 197 + coarse 270x3)"),
+    "cfg3": dict(stage="fine", model=dict(depth=6, heads=8, num_coarse_quantizers=3, num_fine_quantizers=5), shapes=[(12,), (254, 3), (1269,)], batch=8, N=2048,
+                 n_pred=1270, name="musiclm_small fine-stage training step (BASELINE.json configs[2]): d=1024 L=6 h=8, N=2048 "
+                                   "(clap 12 + coarse 254x3 + fine 1269 flattened: remainder heads), batch 8"),
+    "cfg4": dict(stage="coarse", model=dict(depth=24, heads=16, num_coarse_quantizers=3), shapes=[(12,), (197,), (270, 3)], batch=16, N=1024, n_pred=811,
+                 name="musiclm_large coarse-stage training step (BASELINE.json configs[3]: 16 per GPU, global 128 at 8 GPUs): "
+                      "d=1024 L=24 h=16 conv-FFN F=2730, N=1024"),
+}
 METRIC = "coarse-stage training tokens/sec (positions fed to the transformer per optimiser step / step time)"
+SEQ_N = WORKLOADS["cfg2"]["N"]
 
 
-def synth_batch(B, gen):
+def synth_batch(B, gen, shapes=None):
     import torch
-    return [torch.randint(0, 1024, (B, SHAPES["clap"]), generator=gen),
-            torch.randint(0, 1024, (B, SHAPES["semantic"]), generator=gen),
-            torch.randint(0, 1024, (B,) + SHAPES["coarse"], generator=gen)]
+    shapes = shapes or WORKLOADS["cfg2"]["shapes"]
+    return [torch.randint(0, 1024, (B,) + tuple(s), generator=gen) for s in shapes]
 
 
-def flops_per_step(B, N=SEQ_N, L=6, h=8, d=1024):
+def make_model(wl):
+    import open_musiclm_b200 as O
+    fn = {"coarse": O.create_coarse_transformer, "fine": O.create_fine_transformer, "semantic": O.create_semantic_transformer}[wl["stage"]]
+    return fn(**COMMON, **wl["model"])
+
+
+def flops_per_step(B, N=SEQ_N, L=6, h=8, d=1024, n_pred=811):
+    """ALGORITHMIC flops: F = 2730 and C = 1025, not the padded tile sizes."""
     F = int(d * 8 / 3)
     G = 2 * d * (h * 64) + 2 * d * 128 + 2 * (h * 64) * d + 2 * d * 2 * F + 2 * F * d
     A = 2 * 64 * h * (N + 1)
     fwd_attn_ffn = B * N * L * (G + A)
     conv = B * N * L * 2 * 3 * 2 * F
-    logits = B * 811 * 2 * 1025 * d
+    logits = B * n_pred * 2 * 1025 * d
     fwd = fwd_attn_ffn + conv + logits
-    return dict(fwd_attn_ffn=fwd_attn_ffn, fwd=fwd, step=3 * fwd)
+    return dict(fwd_attn_ffn=fwd_attn_ffn, fwd=fwd, step=3 * fwd, gemm_fwd=B * N * L * G + logits)
+
+
+def wl_flops(wl, B):
+    return flops_per_step(B, N=wl["N"], L=wl["model"]["depth"], h=wl["model"]["heads"], n_pred=wl["n_pred"])
+
+
+def cpu_model_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
 
 
 def load_peaks():
@@ -193,7 +224,7 @@ def run_reference(args):
         "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "musiclm_small coarse-stage training step, N=1024 (BASELINE.json configs[1]), CPU sample batch 2"},
-        "cpu_baseline": {"value": r["tokens_per_s"], "unit": "tokens/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "cpu_baseline": {"value": r["tokens_per_s"], "unit": "tokens/s", "cores": r["cores"], "cpu_model": cpu_model_name(), "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["tokens_per_s"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -201,6 +232,172 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+class Instrument:
+    """Kernel-launch accounting and one CUDA-event pair per GEMM-family launch (off during the timed regions)."""
+    kernels_per_call = {"omlm_attn_bwd": 2, "omlm_attn_bwd_tc": 2, "omlm_ffn_mid_bwd": 2}
+
+    def __init__(self):
+        import torch
+        from open_musiclm_b200 import lib
+        import open_musiclm_b200.engine as eng_mod
+        self.torch, self.lib = torch, lib
+        self.launches, self.on, self.log, self.dims = 0, False, [], {}
+        orig_call, orig_gemm, orig_up = lib.call, lib.gemm, lib.gemm_ffn_up
+
+        def counting_call(name, *a):
+            self.launches += self.kernels_per_call.get(name, 1)
+            return orig_call(name, *a)
+
+        def alg(v):       # padded tile dimension -> the algorithmic one (Fp -> F, 2 Fp -> 2 F, Cp -> C)
+            return self.dims.get(v, v)
+
+        def timed_gemm(a, b, out, **kw):
+            if not self.on:
+                return orig_gemm(a, b, out, **kw)
+            a_mn, b_mn = kw.get("a_mn", False), kw.get("b_mn", False)
+            M = kw.get("M") or (a.shape[1] if a_mn else a.shape[0])
+            K = kw.get("K") or (a.shape[0] if a_mn else a.shape[1])
+            Nn = kw.get("N") or (b.shape[1] if b_mn else b.shape[0])
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); r = orig_gemm(a, b, out, **kw); e1.record()
+            self.log.append((e0, e1, 2.0 * alg(M) * alg(Nn) * alg(K)))
+            return r
+
+        def timed_ffn_up(xn, w1p, cwp, u, h, rowsum, Nseq, Fp, **kw):   # the FFN-up GEMM (conv + GEGLU fused in its epilogue)
+            if not self.on:
+                return orig_up(xn, w1p, cwp, u, h, rowsum, Nseq, Fp, **kw)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); r = orig_up(xn, w1p, cwp, u, h, rowsum, Nseq, Fp, **kw); e1.record()
+            self.log.append((e0, e1, 2.0 * xn.shape[0] * alg(2 * Fp) * xn.shape[1]))
+            return r
+        lib.call = counting_call
+        lib.gemm = eng_mod.lib.gemm = timed_gemm
+        lib.gemm_ffn_up = eng_mod.lib.gemm_ffn_up = timed_ffn_up
+
+    def set_dims(self, eng):
+        self.dims = {eng.Fp: eng.F, 2 * eng.Fp: 2 * eng.F}
+        for c, cp in zip(eng.C, eng.Cp):
+            self.dims[cp] = c
+
+
+def measure(key, args, world, rank, local, inst, full):
+    """Times one workload.  full: the headline treatment (e2e loop, per-launch GEMM events, forward-only, re-check);
+    otherwise device-timed steps + forward only (the other BASELINE configs reported beside the headline)."""
+    import torch
+    import torch.distributed as dist
+    import open_musiclm_b200 as O
+    wl = WORKLOADS[key]
+    B = args.batch if (full and args.batch) else wl["batch"]
+    steps = args.steps if full else max(5, min(args.steps, 10))
+    torch.manual_seed(0)                                      # identical init on every rank (= the reference's init)
+    model = make_model(wl).cuda()
+    tr = O.HotPathTrainer(model, cross_entropy_loss_weights=TRAIN["ce_weights"], lr=TRAIN["lr"], lr_warmup=TRAIN["lr_warmup"],
+                          wd=TRAIN["wd"], max_grad_norm=TRAIN["max_grad_norm"], grad_accum_every=1, seed=rank)
+    inst.set_dims(tr.eng)
+    gen = torch.Generator().manual_seed(1234 + rank)
+    pool_host = [[t.pin_memory() for t in synth_batch(B, gen, wl["shapes"])] for _ in range(8)]
+    pool_dev = [[t.cuda() for t in b] for b in pool_host]
+    h2d = sum(t.numel() * t.element_size() for t in pool_host[0])
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n, finish=None):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        if finish is not None:
+            finish()
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / n
+
+    step_dev = lambda i: tr.train_step([pool_dev[i % len(pool_dev)]])
+    # first step: eager launches, counted (the CUDA graph captured two steps later replays exactly these kernels)
+    inst.launches = 0
+    step_dev(0)
+    n_launch = inst.launches
+    for i in range(max(args.warmup, 3)):
+        step_dev(i + 1)
+    sampler = ClockSampler(local) if (full and rank == 0) else None
+    if sampler:
+        sampler.start()
+    ms_step = timed(step_dev, steps)
+    fl = wl_flops(wl, B)
+    peaks = load_peaks()
+    tok = world * B * wl["N"]
+    res = dict(key=key, B=B, tok=tok, ms_step=ms_step, n_launch=n_launch, fl=fl, steps=steps, h2d=h2d, tr=tr)
+    if full:
+        # end to end through the public trainer API: every step copies its batch from pinned host memory and its loss back
+        # to the host; the loss of step i is read on the host while step i+1 runs (one-step logging lag), the last one
+        # before the timed region closes
+        pending, host_losses = [], []
+
+        def step_e2e(i):
+            pending.append(tr.train_step_async([pool_host[i % len(pool_host)]]))
+            if len(pending) > 1:
+                host_losses.append(pending.pop(0).value())
+
+        def drain_e2e():
+            while pending:
+                host_losses.append(pending.pop(0).value())
+        for i in range(2):
+            step_e2e(i)
+        drain_e2e()
+        host_losses.clear()
+        res["ms_e2e"] = timed(step_e2e, steps, finish=drain_e2e)
+        assert len(host_losses) == steps and all(math.isfinite(v) for v in host_losses), "e2e: every step's loss must reach the host"
+        res["clocks"] = sampler.stop() if sampler else None
+        # ---- instrumented steps: GEMM family (the dominant kernel) with one CUDA-event pair per launch
+        graph_was = tr.use_cuda_graph
+        tr.use_cuda_graph = False            # per-launch CUDA events need eager launches (same kernels, same order)
+        step_dev(0)
+        inst.log.clear()
+        inst.on = True
+        res["ms_instr"] = timed(step_dev, steps)
+        inst.on = False
+        tr.use_cuda_graph = graph_was
+        torch.cuda.synchronize()
+        res["g_ms"] = sum(e0.elapsed_time(e1) for e0, e1, _ in inst.log)
+        res["g_fl"] = sum(f for _, _, f in inst.log)
+        res["n_gemm"] = len(inst.log) // steps
+    # forward-only (attention + FFN + heads, eval): the north_star's forward roofline figure
+    fwd_fn = lambda i: tr.eval_loss(pool_dev[i % len(pool_dev)])
+    for i in range(3):
+        fwd_fn(i)
+    res["ms_fwd"] = timed(fwd_fn, steps)
+    if full:
+        # order check: the device loop again, now after the e2e and instrumented loops (same K), to expose any
+        # power-cap / clock drift between the first and the later timed regions
+        for i in range(2):
+            step_dev(i)
+        res["ms_step_again"] = timed(step_dev, steps)
+    res["graph"] = tr.use_cuda_graph
+    res["overlap"] = getattr(tr, "allreduce_mode", None)
+    res["peaks"] = peaks
+    return res
+
+
+def summary(res):
+    """Sub-result for a BASELINE config reported beside the headline."""
+    fl, pk = res["fl"], res["peaks"]
+    tps = res["tok"] / (res["ms_step"] * 1e-3)
+    return {"workload": WORKLOADS[res["key"]]["name"], "per_gpu_batch": res["B"], "seq_len": WORKLOADS[res["key"]]["N"],
+            "tokens_per_s": tps, "ms_per_step": res["ms_step"], "steps": res["steps"],
+            "step_tflops_per_gpu": fl["step"] / (res["ms_step"] * 1e-3) / 1e12,
+            "step_frac_of_sustained_peak": fl["step"] / (res["ms_step"] * 1e-3) / 1e12 / pk["sustained"],
+            "forward_ms": res["ms_fwd"], "forward_attn_ffn_frac_of_sustained_peak": fl["fwd_attn_ffn"] / (res["ms_fwd"] * 1e-3) / 1e12 / pk["sustained"],
+            "forward_attn_ffn_frac_of_burst_peak": fl["fwd_attn_ffn"] / (res["ms_fwd"] * 1e-3) / 1e12 / pk["burst"],
+            "gpu_launches_per_step": res["n_launch"]}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -211,178 +408,86 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun for N > 1"
-    import open_musiclm_b200 as O
-    from open_musiclm_b200 import lib
-
-    B = args.batch
-    torch.manual_seed(0)                                      # identical init on every rank (= the reference's init)
-    model = O.create_coarse_transformer(**CFG).cuda()
-    tr = O.HotPathTrainer(model, cross_entropy_loss_weights=TRAIN["ce_weights"], lr=TRAIN["lr"], lr_warmup=TRAIN["lr_warmup"],
-                          wd=TRAIN["wd"], max_grad_norm=TRAIN["max_grad_norm"], grad_accum_every=1, seed=rank)
-    gen = torch.Generator().manual_seed(1234 + rank)
-    pool_host = [[t.pin_memory() for t in synth_batch(B, gen)] for _ in range(8)]
-    pool_dev = [[t.cuda() for t in b] for b in pool_host]
-    h2d = sum(t.numel() * t.element_size() for t in pool_host[0])
-
-    # kernel-launch accounting + GEMM event instrumentation (off during the timed `value` region)
-    launches = {"n": 0}
-    kernels_per_call = {"omlm_attn_bwd": 2, "omlm_ffn_mid_bwd": 2}
-    orig_call = lib.call
-
-    def counting_call(name, *a):
-        launches["n"] += kernels_per_call.get(name, 1)
-        return orig_call(name, *a)
-    lib.call = counting_call
-    gemm_log = []
-    orig_gemm = lib.gemm
-    instrument = {"on": False}
-
-    def timed_gemm(a, b, out, **kw):
-        if not instrument["on"]:
-            return orig_gemm(a, b, out, **kw)
-        a_mn, b_mn = kw.get("a_mn", False), kw.get("b_mn", False)
-        M = kw.get("M") or (a.shape[1] if a_mn else a.shape[0])
-        K = kw.get("K") or (a.shape[0] if a_mn else a.shape[1])
-        Nn = kw.get("N") or (b.shape[1] if b_mn else b.shape[0])
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); r = orig_gemm(a, b, out, **kw); e1.record()
-        gemm_log.append((e0, e1, 2.0 * M * Nn * K))
-        return r
-    lib.gemm = timed_gemm
-    orig_ffn_up = lib.gemm_ffn_up
-
-    def timed_ffn_up(xn, w1p, cwp, u, h, rowsum, Nseq, Fp, **kw):   # the FFN-up GEMM (conv + GEGLU fused in its epilogue)
-        if not instrument["on"]:
-            return orig_ffn_up(xn, w1p, cwp, u, h, rowsum, Nseq, Fp, **kw)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); r = orig_ffn_up(xn, w1p, cwp, u, h, rowsum, Nseq, Fp, **kw); e1.record()
-        gemm_log.append((e0, e1, 2.0 * xn.shape[0] * (2 * Fp) * xn.shape[1]))
-        return r
-    lib.gemm_ffn_up = timed_ffn_up
-    import open_musiclm_b200.engine as eng_mod
-    eng_mod.lib.gemm = timed_gemm
-    eng_mod.lib.gemm_ffn_up = timed_ffn_up
-
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, finish=None):
-        sync_all()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            fn(i)
-        if finish is not None:
-            finish()
-        e1.record()
-        sync_all()
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms) / steps
-
-    step_dev = lambda i: tr.train_step([pool_dev[i % len(pool_dev)]])
-    # end to end through the public trainer API: every step copies its batch from pinned host memory and its loss back
-    # to the host; the loss of step i is read on the host while step i+1 runs (one-step logging lag), the last one
-    # before the timed region closes
-    pending, host_losses = [], []
-
-    def step_e2e(i):
-        pending.append(tr.train_step_async([pool_host[i % len(pool_host)]]))
-        if len(pending) > 1:
-            host_losses.append(pending.pop(0).value())
-
-    def drain_e2e():
-        while pending:
-            host_losses.append(pending.pop(0).value())
-
-    # first step: eager launches, counted (the CUDA graph captured two steps later replays exactly these kernels)
-    launches["n"] = 0
-    step_dev(0)
-    n_launch = launches["n"]
-    for i in range(max(args.warmup, 3)):
-        step_dev(i + 1)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ms_step = timed(step_dev, args.steps)
-    for i in range(2):
-        step_e2e(i)
-    drain_e2e()
-    host_losses.clear()
-    ms_e2e = timed(step_e2e, args.steps, finish=drain_e2e)
-    assert len(host_losses) == args.steps and all(math.isfinite(v) for v in host_losses), "e2e: every step's loss must reach the host"
-    clocks = sampler.stop() if rank == 0 else None
-
-    # ---- instrumented steps: GEMM family (the dominant kernel) with one CUDA-event pair per launch
-    graph_was = tr.use_cuda_graph
-    tr.use_cuda_graph = False            # per-launch CUDA events need eager launches (same kernels, same order)
-    step_dev(0)
-    instrument["on"] = True
-    ms_instr = timed(step_dev, args.steps)
-    instrument["on"] = False
-    tr.use_cuda_graph = graph_was
-    torch.cuda.synchronize()
-    g_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in gemm_log)
-    g_fl = sum(f for _, _, f in gemm_log)
-    n_gemm = len(gemm_log) // args.steps
-    # forward-only (attention + FFN + heads, eval): the north_star's forward roofline figure
-    fwd_fn = lambda i: tr.eval_loss(pool_dev[i % len(pool_dev)])
-    for i in range(3):
-        fwd_fn(i)
-    ms_fwd = timed(fwd_fn, args.steps)
-
-    # order check: the device loop again, now after the e2e and instrumented loops (same K), to expose any
-    # power-cap / clock drift between the first and the later timed regions
-    for i in range(2):
-        step_dev(i)
-    ms_step_again = timed(step_dev, args.steps)
+    inst = Instrument()
+    res = measure(args.config, args, world, rank, local, inst, full=True)
+    tr = res.pop("tr")
+    extras = {}
+    del tr
+    torch.cuda.empty_cache()
+    for key in [k for k in args.extra.split(",") if k and k != "none" and k != args.config]:
+        r = measure(key, args, world, rank, local, inst, full=False)
+        r.pop("tr")
+        extras[key] = summary(r)
+        torch.cuda.empty_cache()
     gemm_traffic = {}
     try:   # DRAM bytes of the GEMM family from the committed ncu --set full capture (tools/ncu_summarize.py)
-        gemm_traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_gemm_traffic.json")))
+        gemm_traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_gemm_traffic.json")))
     except (OSError, ValueError):
-        pass
-    fl = flops_per_step(B)
-    peaks = load_peaks()
-    tok = world * B * SEQ_N
+        try:
+            gemm_traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_gemm_traffic.json")))
+        except (OSError, ValueError):
+            pass
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         r = cpu_reference_arm(steps=3, warmup=1, budget_s=60.0)
-        cpu = {"value": r["tokens_per_s"], "unit": "tokens/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        cpu = {"value": r["tokens_per_s"], "unit": "tokens/s", "cores": r["cores"], "cpu_model": cpu_model_name(), "kind": "port", "sample": r["sample"],
+               "cfg1_forward": cpu_cfg1_forward(r["cores"])}
     if rank == 0:
-        ach = g_fl / (g_ms * 1e-3) / 1e12
+        wl, fl, peaks = WORKLOADS[args.config], res["fl"], res["peaks"]
+        ms_step, ms_fwd, tok, B = res["ms_step"], res["ms_fwd"], res["tok"], res["B"]
+        ach = res["g_fl"] / (res["g_ms"] * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": tok / (ms_step * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "ms_per_step_recheck_after_e2e": ms_step_again, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "musiclm_small coarse-stage training step (BASELINE.json configs[1]): d=1024 L=6 h=8 conv-FFN F=2730, "
-                                   "N=1024 (clap 12 + semantic 197 + coarse 270x3), dropout 0.1 + forgetful mask 0.15, AdamW + clip 0.5",
-                       "global_batch": world * B, "per_gpu_batch": B, "seq_len": SEQ_N, "parallelism": f"dp{world}",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "ms_per_step_recheck_after_e2e": res["ms_step_again"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 (fp16 operands for the forward GEMMs on LayerNorm outputs x weights; fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": wl["name"] + ", dropout 0.1 + forgetful mask 0.15, AdamW + clip 0.5",
+                       "global_batch": world * B, "per_gpu_batch": B, "seq_len": wl["N"], "parallelism": f"dp{world}",
                        "l2": "no explicit flush: one step touches > 3 GB of activations/weights, far above the 126 MB L2"},
-            "e2e": {"value": tok / (ms_e2e * 1e-3), "unit": "tokens/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+            "e2e": {"value": tok / (res["ms_e2e"] * 1e-3), "unit": "tokens/s", "ms_per_step": res["ms_e2e"], "h2d_bytes_per_step": res["h2d"],
                     "d2h_bytes_per_step": 4,
                     "api": "HotPathTrainer.train_step_async: batch copied from pinned host memory every step, loss copied "
                            "to pinned host memory every step and read on the host one step later (last one inside the timed region)"},
-            "gpu_launches": n_launch * args.steps, "gpu_launches_per_step": n_launch,
-            "launch_mode": "step replayed from two CUDA graphs (fwd+bwd | clip+AdamW+pack), NCCL all-reduce eager between them" if tr.use_cuda_graph else "eager launches",
+            "gpu_launches": res["n_launch"] * args.steps, "gpu_launches_per_step": res["n_launch"],
+            "launch_mode": ("step replayed from CUDA graphs; gradient all-reduce: " + str(res["overlap"])) if res["graph"] else "eager launches",
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel + gemm_ffn_up_kernel (tcgen05; all operand-major variants; FFN-up time includes its fused conv+GEGLU epilogue)", "achieved": ach,
-                         "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": ach / peaks["sustained"], "traffic": gemm_traffic.get("bytes_per_launch"), "traffic_unit": "bytes per launch (family average)", "traffic_source": gemm_traffic.get("source"),
+                         "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": ach / peaks["sustained"], "frac_of_burst_peak": ach / peaks["burst"],
+                         "flops": "algorithmic (F = 2730, C = 1025; padded tile columns not counted)",
+                         "traffic": gemm_traffic.get("bytes_per_launch"), "traffic_unit": "bytes per launch (family average)", "traffic_source": gemm_traffic.get("source"),
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']})",
-                         "launches_per_step": n_gemm, "gemm_ms_per_step": g_ms / args.steps,
-                         "gemm_share_of_step": (g_ms / args.steps) / ms_instr, "ms_per_step_instrumented": ms_instr},
+                         "launches_per_step": res["n_gemm"], "gemm_ms_per_step": res["g_ms"] / args.steps,
+                         "gemm_share_of_step": (res["g_ms"] / args.steps) / res["ms_instr"], "ms_per_step_instrumented": res["ms_instr"]},
             "step_model_flops": {"tflop_per_step_per_gpu": fl["step"] / 1e12, "achieved_tflops_per_gpu": fl["step"] / (ms_step * 1e-3) / 1e12,
                                  "frac_of_sustained_peak": fl["step"] / (ms_step * 1e-3) / 1e12 / peaks["sustained"]},
             "forward_only": {"ms": ms_fwd, "attn_ffn_tflops": fl["fwd_attn_ffn"] / (ms_fwd * 1e-3) / 1e12,
                              "attn_ffn_frac_of_peak": fl["fwd_attn_ffn"] / (ms_fwd * 1e-3) / 1e12 / peaks["sustained"],
+                             "attn_ffn_frac_of_burst_peak": fl["fwd_attn_ffn"] / (ms_fwd * 1e-3) / 1e12 / peaks["burst"],
                              "attn_ffn_frac_of_nominal_2250": fl["fwd_attn_ffn"] / (ms_fwd * 1e-3) / 1e12 / 2250.0},
-            "clocks": clocks,
+            "configs": extras,
+            "clocks": res["clocks"],
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def cpu_cfg1_forward(cores):
+    """BASELINE configs[0]: musiclm_small semantic-stage forward on the host cores, batch 2, N = 256 (oracle port, fp32,
+    eval), median of 5 after 2 warm-ups."""
+    import torch
+    from oracle import restatement as R
+    torch.set_num_threads(cores)
+    cfg = R.semantic_cfg(ce_weights=[0.0, 1.0])
+    sd = R.init_state(cfg, seed=0)
+    g = torch.Generator().manual_seed(1234)
+    toks = [torch.randint(0, 1024, (2, 12), generator=g).numpy(), torch.randint(0, 1024, (2, 241), generator=g).numpy()]
+    ids, mask, _ = R.prepare_ids(cfg, toks, True, None)
+    ts = []
+    with torch.no_grad():
+        for i in range(7):
+            t0 = time.perf_counter(); R.forward_logits(cfg, sd, ids, mask); ts.append(time.perf_counter() - t0)
+    ts = sorted(ts[2:])
+    return {"tokens_per_s": 2 * 256 / ts[len(ts) // 2], "ms": ts[len(ts) // 2] * 1e3, "workload": "configs[0]: semantic forward, B=2, N=256, fp32"}
 
 
 def main():
@@ -391,7 +496,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="per-GPU batch (BASELINE configs[1]: 16)")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch of the headline workload (0 = the config's own: 16 / 8 / 16)")
+    ap.add_argument("--config", default="cfg2", choices=sorted(WORKLOADS), help="headline workload (default: BASELINE configs[1])")
+    ap.add_argument("--extra", default="cfg3,cfg4", help="other BASELINE configs timed beside it (sub-results under 'configs'); 'none' to skip")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define OMLM_B200_ABI_VERSION 1
+#define OMLM_B200_ABI_VERSION 2
 #define OMLM_MAX_SEQS 4
 
 const char* omlm_last_error(void);
@@ -38,6 +38,15 @@ int omlm_gemm_bf16(const void* A, int a_mn_major, long lda, const void* B, int b
                    int M, int N, int K, void* out, int out_f32, long ldo, const float* addend,
                    long ldadd, float alpha, int splits, int row_split, int row_valid, int n_valid,
                    int block_n, int max_ctas, void* stream);
+/* The same GEMM with the 16-bit operand format selectable: a_f16 = b_f16 = 1 -> IEEE fp16 operands, 0 -> bf16 (same
+ * tensor rate, fp32 accumulation).  B200 raises an illegal-instruction fault when the two formats differ (measured), so
+ * a_f16 != b_f16 is rejected.  The hot path uses fp16 for the forward GEMMs whose operands are bounded by
+ * construction (LayerNorm outputs x weights, FFN activations) and bf16 wherever a gradient or the raw residual stream
+ * is an operand. */
+int omlm_gemm16(const void* A, int a_f16, int a_mn_major, long lda, const void* B, int b_f16, int b_mn_major, long ldb,
+                int M, int N, int K, void* out, int out_f32, long ldo, const float* addend,
+                long ldadd, float alpha, int splits, int row_split, int row_valid, int n_valid,
+                int block_n, int max_ctas, void* stream);
 
 /* ---- integer token path (bit-exact) ------------------------------------------------------------
  * One pass over the raw ids of all sequences of a TokenConditionedTransformer batch.
@@ -48,13 +57,15 @@ int omlm_gemm_bf16(const void* A, int a_mn_major, long lda, const void* B, int b
  * (t mod q) added BEFORE the pad test, open_musiclm.py:126-133, utils.py:133-138; -1 = zero row;
  * start tokens are extra rows) and the key mask (AND mask_in AND forget_keep when given, :373-376).
  *   ids[s]: int64 [B, len[s]] device pointers (host array of n_seqs pointers)
- *   ids_out int64 [B, sum n_tok]; src_row int32 [B, N]; key_mask u8 [B, N]; labels int32 [B, sum(len+eos)] or NULL. */
+ *   ids_out int64 [B, sum n_tok]; src_row int32 [B, N]; key_mask u8 [B, N]; labels int32 [B, sum(len+eos)] or NULL.
+ *   err_flag (device int, optional): bit s is set when sequence s holds an id outside its embedding table (where
+ *   nn.Embedding would raise); such positions get the zero embedding instead of an out-of-bounds read. */
 int omlm_token_plan(int n_seqs, const long long* const* ids, const int* len, const int* codebook,
                     const int* nq, const int* emb_row_base, const int* start_row, int B,
                     int append_eos, int drop_last, int mask_cond, int pad_id,
                     const unsigned char* mask_in, const unsigned char* forget_keep,
                     long long* ids_out, int* src_row, unsigned char* key_mask, int* labels,
-                    void* stream);
+                    int* err_flag, void* stream);
 /* Forgetful causal mask (utils.py:49-56): keep[b,p]=0 for a uniformly random subset of num_drop
  * positions per row, never position 0.  seed: device pointer; stream_id separates draws. */
 int omlm_forgetful_mask(unsigned char* keep, int B, int N, int num_drop,
@@ -66,11 +77,12 @@ int omlm_embed_scatter_add(float* dtable, const int* src_row, const float* dx, i
                            float scale, void* stream);
 
 /* ---- normalisation ------------------------------------------------------------------------------
- * Bias-less LayerNorm (transformer.py:24-31).  x fp32 [M,D] -> y bf16 [M,D] (row m written to row
+ * Bias-less LayerNorm (transformer.py:24-31).  x fp32 [M,D] -> y [M,D] in fp16 (y_f16 = 1) or bf16 (row m written to row
  * dest_row[m] when given, skipped if negative), optional raw bf16 copy of x (keys/values are
- * projected from the un-normalised stream, transformer.py:228,254), stats[m] = (mean, rstd). */
-int omlm_layernorm_fwd(const float* x, const float* gamma, void* y_bf16, void* xraw_bf16, float* stats,
-                       const int* dest_row, int M, int D, void* stream);
+ * projected from the un-normalised stream, transformer.py:228,254), stats[m] = (mean, rstd).  ycopy_bf16 (optional):
+ * a bf16 copy of y for the weight-gradient GEMMs (tcgen05 needs both operands in one format; gradients are bf16). */
+int omlm_layernorm_fwd(const float* x, const float* gamma, void* y16, int y_f16, void* ycopy_bf16, void* xraw_bf16,
+                       float* stats, const int* dest_row, int M, int D, void* stream);
 /* dx = [dres] + [draw] + LN-backward(dy);  dgamma += sum_rows dy * xhat.  dy row for x row m is
  * src_row[m] when given (-1: no gradient).  dx_bf16 (optional): bf16 copy of dx for the next GEMMs. */
 int omlm_layernorm_bwd(const void* dy_bf16, const float* x, const float* stats, const float* gamma,
@@ -113,10 +125,11 @@ int omlm_attn_bwd(const void* qn, const void* kvn, const void* d_o, const void* 
                   float* dqn, float* dkvn, float* dtable, int B, int N, int heads, float scale,
                   void* stream);
 
-/* tcgen05/TMEM/TMA backward.  ds_scratch: bf16 [B, N*heads, round_up(N,128)] (dS tiles for the bias-gradient pass). */
+/* tcgen05/TMEM/TMA backward (same contract; the bias gradient -- diagonal sums of dS -- is formed inside the kernel from
+ * an fp32-class hi/lo split of dS, no scratch tensor). */
 int omlm_attn_bwd_tc(const void* qn, const void* kvn, const void* d_o, const void* o, const float* lse2,
                      const float* table, int table_ld, const unsigned char* key_mask, float* dsum_scratch,
-                     void* ds_scratch, float* dqn, float* dkvn, float* dtable, int B, int N, int heads,
+                     float* dqn, float* dkvn, float* dtable, int B, int N, int heads,
                      float scale, void* stream);
 
 /* ---- ConvFeedForward (transformer.py:122-150) ---------------------------------------------------
@@ -124,19 +137,23 @@ int omlm_attn_bwd_tc(const void* qn, const void* kvn, const void* d_o, const voi
  * [128 value | 128 gate]; h / hn / gamma / W2 columns are in natural channel order (zero padded to Fp).
  * FFN up-projection GEMM (tcgen05) with the causal depthwise conv (k=3), GEGLU (exact erf) and the LayerNorm row
  * statistics fused into its epilogue:  u bf16 [M, 2Fp], h bf16 [M, Fp], rowsum fp32 [M, Fp/128, 2] = per-128-channel
- * partial (sum h, sum h^2), plain stores (no zeroing needed; summed in a fixed order by omlm_ffn_norm_fwd).  M = B * Nseq rows, sequences of Nseq consecutive rows. */
+ * partial (sum h, sum h^2), plain stores (no zeroing needed; summed in a fixed order by omlm_ffn_norm_fwd).  M = B * Nseq rows, sequences of Nseq consecutive rows.
+ * act_f16 = 1: xn, w1 are fp16 operands and the forward activations u, h, hn are fp16 (0: all bf16); the same flag
+ * must be given to omlm_ffn_norm_fwd (h, hn) and omlm_ffn_mid_bwd (u).  Gradients (dhn, du) and the hn that
+ * omlm_ffn_mid_bwd reads (omlm_ffn_norm_fwd's hn_copy_bf16 when act_f16) are always bf16. */
 int omlm_gemm_ffn_up(const void* xn, const void* w1_packed, const float* conv_w_packed, void* u_out, void* h_out,
-                     float* rowsum, int M, int Nseq, int K, int Fp, int max_ctas, void* stream);
+                     float* rowsum, int M, int Nseq, int K, int Fp, int act_f16, int max_ctas, void* stream);
 /* hn = dropout(LayerNorm_F(h)) from the fused statistics; stats fp32 [M, 2] = (mean, rstd) for the backward pass.
  * With drop_p > 0 the Philox keep mask is also written to keep_bits (uint8 [M, Fp/8], bit i of byte j = channel 8j+i)
  * so the backward pass reads 1 bit per element instead of regenerating the random stream. */
-int omlm_ffn_norm_fwd(const void* h, const float* rowsum, const float* gamma, void* hn, float* stats, void* keep_bits,
-                      long M, int F, int Fp, float drop_p, const unsigned long long* seed, int layer, void* stream);
+int omlm_ffn_norm_fwd(const void* h, const float* rowsum, const float* gamma, void* hn, void* hn_copy_bf16, float* stats,
+                      void* keep_bits, long M, int F, int Fp, float drop_p, const unsigned long long* seed, int layer,
+                      int act_f16, void* stream);
 /* dhn, hn (saved forward output), keep_bits (from omlm_ffn_norm_fwd; may be NULL when drop_p == 0) ->
  * du bf16 [B*N, 2Fp]; dgamma [Fp] += ; dconv_w [2Fp,3] += ; rowstat_scratch fp32 [B*N, 2]. */
 int omlm_ffn_mid_bwd(const void* dhn, const void* hn, const void* u, const float* stats, const float* conv_w,
                      const float* gamma, const void* keep_bits, float* rowstat_scratch, void* du, float* dgamma,
-                     float* dconv_w, int B, int N, int F, int Fp, float drop_p, void* stream);
+                     float* dconv_w, int B, int N, int F, int Fp, float drop_p, int act_f16, void* stream);
 
 /* ---- cross entropy (open_musiclm.py:401) --------------------------------------------------------
  * loss_acc[0] += sum of row losses, loss_acc[1] += rows counted; dlogits bf16 [rows, ldd] =
@@ -153,15 +170,15 @@ int omlm_adamw_step(float* p, const float* g, float* m, float* v, long n, long n
                     const double* sumsq, void* stream);
 /* One launch for a whole table of omlm_pack jobs (the per-step refresh of the packed bf16 weights).  The table is
  * DEVICE memory; unit_start = running sum of ceil(rows_p * ceil(cols_p/4) / 256) over the preceding jobs,
- * total_units = that sum over all jobs.  njobs <= 64. */
+ * total_units = that sum over all jobs.  njobs <= 512 per table.  dst_fmt: 0 = bf16, 1 = fp32, 2 = fp16. */
 typedef struct {
   const float* src; void* dst;
   long src_ld, dst_ld, unit_start;
-  int rows_valid, cols_valid, rows_p, cols_p, split_dst, split_src, dst_f32, reserved;
+  int rows_valid, cols_valid, rows_p, cols_p, split_dst, split_src, dst_fmt, reserved;
 } omlm_pack_job;
 int omlm_pack_multi(const omlm_pack_job* jobs_device, int njobs, long total_units, void* stream);
 /* canonical fp32 -> padded compute layout (bf16 or fp32) and gradient unpacking (+=). */
-int omlm_pack(const float* src, long src_ld, int rows_valid, int cols_valid, void* dst, int dst_f32, long dst_ld,
+int omlm_pack(const float* src, long src_ld, int rows_valid, int cols_valid, void* dst, int dst_fmt, long dst_ld,
               int rows_p, int cols_p, int split_dst, int split_src, void* stream);
 int omlm_unpack_add(const float* packed, long p_ld, int rows_p, int cols_p, float* dst, long dst_ld, int rows_valid,
                     int cols_valid, int split_dst, int split_src, void* stream);

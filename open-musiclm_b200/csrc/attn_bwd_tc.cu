@@ -1,7 +1,7 @@
 // Fused causal multi-query cosine-sim attention, backward, on tcgen05 / TMEM / TMA.
 //
-// Autograd of transformer.py:304-331 (see attn_bwd.cu for the math).  Folded-row layout: R = N*h query rows
-// per batch element share one K/V head.  Work unit = (batch, 128-key tile, chunk of 128-row query tiles).
+// Autograd of transformer.py:304-331.  Folded-row layout: R = N*h query rows per batch element share one K/V head
+// (row r = i*h + head).  Work unit = (batch, 128-key tile, chunk of 128-row query tiles).  512 threads:
 //
 //   warp 0       TMA producer: K/V tile once, Q/dO tiles through a 2-stage ring
 //   warp 1       tcgen05.mma issuer, five GEMMs per row tile, all M = 128:
@@ -10,26 +10,30 @@
 //                   dK += dS^T Q        (320..383, accumulated,                    A = dS read MN-major)
 //                   dQ  = dS K          (256..319, per tile,                       A = dS read K-major)
 //   warps 2,3    bias-slice (Toeplitz window, causal -inf folded in) + key-mask builders, one tile ahead
-//   warps 4-7    one thread per query row: S/dP rows from TMEM, P = exp2(s - lse), dS = P (dP - D), both written
-//                as bf16 into ONE 128B-swizzled [row][key] smem tile each that serves as K-major and MN-major operand;
-//                the dS tile is also TMA-stored to a global scratch [B, R, Ns] for the bias-gradient pass
-//   warps 8-11   drain dQ (TMEM -> red.global.add.v4.f32), and dK/dV at the end
-//
-// The bias gradient dTable[hh, i-j] = sum dS is a diagonal sum; it is done by a second, bandwidth-bound kernel
-// over the dS scratch (one thread per (head, delta), coalesced along delta, no atomics inside the sums).
+//   warps 4-11   P / dS: one thread per (query row, 64-key half): S/dP from TMEM, P = exp2(s - lse), dS = P (dP - D).
+//                P and dS are written as bf16 into ONE 128B-swizzled [row][key] smem tile each that serves as K-major and
+//                MN-major MMA operand; the rounding residual dS - bf16(dS) goes to a second bf16 tile (dS_lo).  Two warps
+//                per SM sub-partition hide each other's TMEM / MUFU latencies (one warp per sub-partition did not).
+//   warps 12-15  (a) bias gradient: dTable[hh, i-j] += sum dS is a sum along the diagonals of the dS tile.  It is
+//                formed here from dS_hi + dS_lo (fp32-class: these sums cancel heavily, a bf16-rounded dS shows up
+//                amplified in the rel-pos MLP gradient), each thread owning (head, 8-key chunk) and sliding over the
+//                tile's positions with the diagonal bins in registers, then accumulated in a per-CTA shared table that is
+//                flushed to global once;  (b) drain dQ per tile (TMEM -> red.global.add.v4.f32), dK/dV at the end.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "../../include/omlm_b200.h"
 
 namespace omlm {
 
-constexpr int kBtThreads = 384;
+constexpr int kBtThreads = 512;
 constexpr int kBtBQ = 128, kBtBK = 128;
 constexpr float kBtL2e = 1.4426950408889634f;
 
 constexpr int kBoK = 0, kBoV = 16384, kBoQ = 32768 /*2 stages x 16K*/, kBoDO = 65536 /*2 x 16K*/;
-constexpr int kBoP = 98304 /*32K*/, kBoDS = 131072 /*32K*/, kBoKneg = 163840 /*512 B*/, kBoBar = 164352 /*256 B*/;
-constexpr int kBoBias = 164608;   // 2 buffers x h*W floats
+constexpr int kBoP = 98304 /*32K*/, kBoDS = 131072 /*32K: bf16(dS)*/, kBoDSL = 163840 /*32K: bf16(dS - bf16(dS))*/;
+constexpr int kBoKneg = 196608 /*512 B*/, kBoBar = 197120 /*256 B*/;
+constexpr int kBoBias = 197376;   // 2 buffers x h*W floats, then the diagonal-sum table h*Wacc floats
+constexpr int kBtMaxSmem = 232448;
 
 __device__ __forceinline__ void bt_tmem_ld32(uint32_t taddr, float* r) {
   uint32_t* u = reinterpret_cast<uint32_t*>(r);
@@ -52,13 +56,73 @@ __device__ __forceinline__ void bt_red4(float* addr, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// byte offset of 16-byte chunk `ch` (8 keys) of row `row` inside a swizzled [128 rows][128 keys] bf16 tile
+__device__ __forceinline__ uint32_t bt_tile_off(int row, int ch) {
+  return static_cast<uint32_t>((ch >> 3) * 16384 + row * 128 + (((ch & 7) ^ (row & 7)) << 4));
+}
+
+// Diagonal sums of one dS tile, fast path for h = 128 / IPT heads (tile rows = IPT positions x h heads).
+// A thread owns (head hh, 8-key chunk ch) and walks the tile's IPT positions; element (il, key c) belongs to the
+// diagonal i - j = const, i.e. to register bin il - (c % 8) + 7: all indices are static after unrolling.
+template <int IPT>
+__device__ __forceinline__ void bt_diag_fast(const uint8_t* ds_hi, const uint8_t* ds_lo, float* dacc, int Wacc, int tid,
+                                             int base_t) {
+  constexpr int H = 128 / IPT;
+  for (int u = tid; u < 16 * H; u += 128) {
+    const int hh = u % H, ch = u / H;
+    float acc[IPT + 7];
+#pragma unroll
+    for (int k = 0; k < IPT + 7; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int il = 0; il < IPT; ++il) {
+      const uint32_t off = bt_tile_off(il * H + hh, ch);
+      const uint4 a = *reinterpret_cast<const uint4*>(ds_hi + off);
+      const uint4 b = *reinterpret_cast<const uint4*>(ds_lo + off);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 x = unpack_bf16x2(aw[q]), y = unpack_bf16x2(bw[q]);
+        acc[il - 2 * q + 7] += x.x + y.x;       // key 8 ch + 2q
+        acc[il - 2 * q + 6] += x.y + y.y;       // key 8 ch + 2q + 1
+      }
+    }
+    float* dst = dacc + hh * Wacc + base_t + 120 - ch * 8;
+#pragma unroll
+    for (int k = 0; k < IPT + 7; ++k)
+      if (acc[k] != 0.f) atomicAdd(dst + k, acc[k]);
+  }
+}
+
+// Any head count: one thread per tile row, every non-zero element goes to the shared table by itself.
+__device__ __forceinline__ void bt_diag_generic(const uint8_t* ds_hi, const uint8_t* ds_lo, float* dacc, int Wacc, int tid,
+                                                int r0, int R, int h, int i_min0) {
+  const int r = r0 + tid;
+  if (r >= R) return;
+  const int i = r / h, hh = r - i * h;
+  float* dst = dacc + hh * Wacc + (i - i_min0) + 127;
+#pragma unroll 1
+  for (int ch = 0; ch < 16; ++ch) {
+    const uint32_t off = bt_tile_off(tid, ch);
+    const uint4 a = *reinterpret_cast<const uint4*>(ds_hi + off);
+    const uint4 b = *reinterpret_cast<const uint4*>(ds_lo + off);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 x = unpack_bf16x2(aw[q]), y = unpack_bf16x2(bw[q]);
+      const float v0 = x.x + y.x, v1 = x.y + y.y;
+      if (v0 != 0.f) atomicAdd(dst - (ch * 8 + 2 * q), v0);
+      if (v1 != 0.f) atomicAdd(dst - (ch * 8 + 2 * q + 1), v1);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kBtThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
-                   const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmDS,
+                   const __grid_constant__ CUtensorMap tmKV,
                    const float* __restrict__ lse2, const float* __restrict__ dsum, const float* __restrict__ table,
                    int table_ld, const unsigned char* __restrict__ key_mask, float* __restrict__ dqn,
-                   float* __restrict__ dkvn, int N, int h, float scale, int W, int Wd, int tiles_per_chunk,
-                   int units_per_batch) {
+                   float* __restrict__ dkvn, float* __restrict__ dtable, int N, int h, float scale, int W, int Wd,
+                   int Wacc, int tiles_per_chunk, int units_per_batch) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBoBar);
@@ -66,17 +130,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* qdo_full = bars + 1;    // [2]
   uint64_t* qdo_empty = bars + 3;   // [2]
   uint64_t* sd_full = bars + 5;     // S, dP complete in TMEM
-  uint64_t* sd_free = bars + 6;     // S, dP copied to registers (4 warps)
-  uint64_t* pds_full = bars + 7;    // P, dS tiles in smem (4 warps)
+  uint64_t* sd_free = bars + 6;     // S, dP copied to registers (8 warps)
+  uint64_t* pds_full = bars + 7;    // P, dS tiles in smem (8 warps)
   uint64_t* pds_empty = bars + 8;   // dV/dK/dQ MMAs finished reading P, dS
   uint64_t* dq_full = bars + 9;     // dQ tile complete in TMEM
   uint64_t* dq_free = bars + 10;    // dQ tile drained (4 warps)
   uint64_t* b_full = bars + 11;     // [2]
   uint64_t* b_empty = bars + 13;    // [2]
+  uint64_t* diag_free = bars + 15;  // diagonal sums of the dS tile taken (4 warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   float* kneg = reinterpret_cast<float*>(smem + kBoKneg);
   float* bias = reinterpret_cast<float*>(smem + kBoBias);
   const int slice = h * W;
+  float* dacc = bias + 2 * slice;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int R = N * h;
@@ -95,14 +161,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int T = rt_end - rt_begin;
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmKV); tma_prefetch_desc(&tmDS);
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmKV);
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1);
-      mbar_init(&b_full[i], 2); mbar_init(&b_empty[i], 4);
+      mbar_init(&b_full[i], 2); mbar_init(&b_empty[i], 8);
     }
-    mbar_init(sd_full, 1); mbar_init(sd_free, 4); mbar_init(pds_full, 4); mbar_init(pds_empty, 1);
-    mbar_init(dq_full, 1); mbar_init(dq_free, 4);
+    mbar_init(sd_full, 1); mbar_init(sd_free, 8); mbar_init(pds_full, 8); mbar_init(pds_empty, 1);
+    mbar_init(dq_full, 1); mbar_init(dq_free, 4); mbar_init(diag_free, 4);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -112,7 +178,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
       // ------------------------------------------------------------------ TMA producer
       if (lane == 0) {
@@ -193,10 +259,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int i_min = ((rt_begin + t) * kBtBQ) / h;
         const int delta_min = i_min - j0 - (kBtBK - 1);
         float* dst = bias + buf * slice;
-        for (int hh0 = 0; hh0 < h; hh0 += 8) {
-          float v[8][4];
+        for (int hh0 = 0; hh0 < h; hh0 += 4) {
+          float v[4][4];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
+          for (int k = 0; k < 4; ++k) {
             const float* trow = table + min(hh0 + k, h - 1) * table_ld;
 #pragma unroll
             for (int uu = 0; uu < 4; ++uu) {
@@ -206,7 +272,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
           }
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
+          for (int k = 0; k < 4; ++k) {
             if (hh0 + k < h) {
 #pragma unroll
               for (int uu = 0; uu < 4; ++uu) {
@@ -220,16 +286,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (lane == 0) mbar_arrive(&b_full[buf]);
       }
     }
-  } else if (warp < 8) {
-    // -------------------------------------------------------------------- P / dS warpgroup: one thread per query row
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+  } else if (warp < 12) {
+    // -------------------------------------------------------------------- P / dS: one thread per (query row, 64-key half)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    const int half = (warp - 4) >> 2;
     const int quarter = warp & 3;
     const int row_local = quarter * 32 + lane;
-    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    uint8_t* prow = smem + kBoP + row_local * 128;
-    uint8_t* dsrow = smem + kBoDS + row_local * 128;
+    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * 64;
+    uint8_t* prow = smem + kBoP + half * 16384 + row_local * 128;
+    uint8_t* dsrow = smem + kBoDS + half * 16384 + row_local * 128;
+    uint8_t* dslrow = smem + kBoDSL + half * 16384 + row_local * 128;
     const int sw = row_local & 7;
     const float sc2 = scale * kBtL2e;
+    const float* kn = kneg + half * 64;
     for (int t = 0; t < T; ++t) {
       const int buf = t & 1;
       const int r0 = (rt_begin + t) * kBtBQ;
@@ -242,40 +311,43 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(&b_full[buf], (t >> 1) & 1);
       mbar_wait(sd_full, t & 1);
       tc_fence_after();
-      if (t > 0) {
-        // the previous tile's MMAs and the TMA store of dS must be done with the P / dS buffers
-        mbar_wait(pds_empty, (t - 1) & 1);
-        if (threadIdx.x == 128) tma_store_wait_read<0>();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-      }
-      const float* bp = bias + buf * slice + hh * W + (i - i_min) + (kBtBK - 1);
+      const float* bp = bias + buf * slice + hh * W + (i - i_min) + (kBtBK - 1) - half * 64;
 #pragma unroll 1
-      for (int c4 = 0; c4 < 4; ++c4) {   // 32 keys per step
+      for (int c2 = 0; c2 < 2; ++c2) {   // 32 keys per step
         float s[32], dp[32];
-        bt_tmem_ld32(t_s + c4 * 32, s);
-        bt_tmem_ld32(t_s + 128 + c4 * 32, dp);
+        bt_tmem_ld32(t_s + c2 * 32, s);
+        bt_tmem_ld32(t_s + 128 + c2 * 32, dp);
         tmem_ld_wait();
-        if (c4 == 3) {   // S and dP fully in registers: the tensor core may start the next tile's S / dP
+        if (c2 == 1) {   // S and dP fully in registers: the tensor core may start the next tile's S / dP
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(sd_free);
         }
-        uint32_t pp[16], dd[16];
+        uint32_t pp[16], dh[16], dl[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
-          const int c = c4 * 32 + e;
-          const float x0 = fmaf(s[e], sc2, bp[-c] + kneg[c]) - l2;
-          const float x1 = fmaf(s[e + 1], sc2, bp[-c - 1] + kneg[c + 1]) - l2;
+          const int c = c2 * 32 + e;
+          const float x0 = fmaf(s[e], sc2, bp[-c] + kn[c]) - l2;
+          const float x1 = fmaf(s[e + 1], sc2, bp[-c - 1] + kn[c + 1]) - l2;
           const float p0 = bt_ex2(x0), p1 = bt_ex2(x1);
           pp[e >> 1] = pack_bf16x2(p0, p1);
-          dd[e >> 1] = pack_bf16x2(p0 * (dp[e] - dsm), p1 * (dp[e + 1] - dsm));
+          const float d0 = p0 * (dp[e] - dsm), d1 = p1 * (dp[e + 1] - dsm);
+          const uint32_t hi = pack_bf16x2(d0, d1);
+          const float2 hf = unpack_bf16x2(hi);
+          dh[e >> 1] = hi;
+          dl[e >> 1] = pack_bf16x2(d0 - hf.x, d1 - hf.y);
+        }
+        if (c2 == 0 && t > 0) {
+          // the previous tile's MMAs and its diagonal sums must be done with the P / dS buffers
+          mbar_wait(pds_empty, (t - 1) & 1);
+          mbar_wait(diag_free, (t - 1) & 1);
         }
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {   // four 16-byte chunks of 8 keys
-          const int ch = c4 * 4 + q4;      // chunk 0..15 of the 128-key row
-          const int off = (ch >> 3) * 16384 + (((ch & 7) ^ sw) << 4);
+          const int off = ((c2 * 4 + q4) ^ sw) << 4;
           *reinterpret_cast<uint4*>(prow + off) = make_uint4(pp[q4 * 4], pp[q4 * 4 + 1], pp[q4 * 4 + 2], pp[q4 * 4 + 3]);
-          *reinterpret_cast<uint4*>(dsrow + off) = make_uint4(dd[q4 * 4], dd[q4 * 4 + 1], dd[q4 * 4 + 2], dd[q4 * 4 + 3]);
+          *reinterpret_cast<uint4*>(dsrow + off) = make_uint4(dh[q4 * 4], dh[q4 * 4 + 1], dh[q4 * 4 + 2], dh[q4 * 4 + 3]);
+          *reinterpret_cast<uint4*>(dslrow + off) = make_uint4(dl[q4 * 4], dl[q4 * 4 + 1], dl[q4 * 4 + 2], dl[q4 * 4 + 3]);
         }
       }
       __syncwarp();
@@ -283,23 +355,27 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
-      // dS tile -> global scratch for the bias-gradient pass (needs the whole tile: all four warps)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 128) {
-        tma_store_3d(&tmDS, smem + kBoDS, j0, r0, b);
-        tma_store_3d(&tmDS, smem + kBoDS + 16384, j0 + 64, r0, b);
-        tma_store_commit();
-      }
     }
-    if (threadIdx.x == 128) tma_store_wait_all();   // the dS scratch must be complete before the grid retires
   } else {
-    // -------------------------------------------------------------------- dQ / dK / dV drain warpgroup
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 136;");
+    // -------------------------------------------------------------------- bias-gradient diagonals + dQ / dK / dV drain
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
     const int quarter = warp & 3;
     const int row_local = quarter * 32 + lane;
+    const int tid = threadIdx.x - 384;
     const uint32_t t_q = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + 256;
+    const int i_min0 = (rt_begin * kBtBQ) / h;
+    for (int i = tid; i < h * Wacc; i += 128) dacc[i] = 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     for (int t = 0; t < T; ++t) {
-      const int r = (rt_begin + t) * kBtBQ + row_local;
+      const int r0 = (rt_begin + t) * kBtBQ;
+      mbar_wait(pds_full, t & 1);
+      if (h == 8) bt_diag_fast<16>(smem + kBoDS, smem + kBoDSL, dacc, Wacc, tid, r0 / h - i_min0);
+      else if (h == 16) bt_diag_fast<8>(smem + kBoDS, smem + kBoDSL, dacc, Wacc, tid, r0 / h - i_min0);
+      else bt_diag_generic(smem + kBoDS, smem + kBoDSL, dacc, Wacc, tid, r0, R, h, i_min0);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(diag_free);
+      // ---- dQ of this tile
+      const int r = r0 + row_local;
       mbar_wait(dq_full, t & 1);
       tc_fence_after();
       float q[64];
@@ -335,28 +411,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int c = 0; c < 64; c += 4) bt_red4(dst + c, a[c], a[c + 1], a[c + 2], a[c + 3]);
     }
     tc_fence_before();
+    // ---- flush the CTA's diagonal sums: table index delta = i - j = delta_base + column
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int delta_base = i_min0 - j0 - (kBtBK - 1);
+    for (int idx = tid; idx < h * Wacc; idx += 128) {
+      const float v = dacc[idx];
+      const int hh = idx / Wacc, delta = delta_base + (idx - hh * Wacc);
+      if (v != 0.f && delta >= 0 && delta < N) atomicAdd(&dtable[hh * table_ld + delta], v);
+    }
   }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
-}
-
-// dTable[hh, delta] += sum_b sum_{i >= delta} dS[b, (i, hh), i - delta]
-// grid: (ceil(N / 256), h, B * ichunks); thread = one delta; coalesced along delta (consecutive keys of one row).
-__global__ void __launch_bounds__(256)
-attn_dbias_kernel(const __nv_bfloat16* __restrict__ ds, long ld_row, long ld_batch, float* __restrict__ dtable,
-                  int table_ld, int N, int h, int ichunk, int n_ichunks) {
-  const int delta = blockIdx.x * 256 + threadIdx.x;
-  const int hh = blockIdx.y;
-  const int b = blockIdx.z / n_ichunks, ic = blockIdx.z - b * n_ichunks;
-  if (delta >= N) return;
-  const int i0 = max(delta, ic * ichunk), i1 = min(N, (ic + 1) * ichunk);
-  float acc = 0.f;
-  const __nv_bfloat16* base = ds + static_cast<long>(b) * ld_batch;
-  for (int i = i0; i < i1; ++i) acc += __bfloat162float(base[static_cast<long>(i * h + hh) * ld_row + (i - delta)]);
-  if (acc != 0.f) atomicAdd(&dtable[hh * table_ld + delta], acc);
 }
 
 // D[r] = sum_d dO[r, d] * O[r, d]
@@ -386,7 +454,7 @@ attn_bwd_tc_dsum_kernel(const __nv_bfloat16* __restrict__ d_o, const __nv_bfloat
 
 extern "C" int omlm_attn_bwd_tc(const void* qn, const void* kvn, const void* d_o, const void* o, const float* lse2,
                                 const float* table, int table_ld, const unsigned char* key_mask, float* dsum_scratch,
-                                void* ds_scratch, float* dqn, float* dkvn, float* dtable, int B, int N, int heads,
+                                float* dqn, float* dkvn, float* dtable, int B, int N, int heads,
                                 float scale, void* stream) {
   using namespace omlm;
   OMLM_CHECK_ARG(B > 0 && N > 0 && heads > 0, "attn_bwd_tc: bad shape");
@@ -401,49 +469,46 @@ extern "C" int omlm_attn_bwd_tc(const void* qn, const void* kvn, const void* d_o
   int W = Wd;
   const int want = (32 % heads == 0) ? (32 / heads) % 32 : 1;
   while ((32 % heads == 0) ? (W % 32 != want) : (W % 2 == 0)) ++W;
-  const int smem_bytes = kBoBias + 2 * heads * W * 4 + 1024;
-  OMLM_CHECK_ARG(smem_bytes <= 232448, "attn_bwd_tc: too many heads (%d)", heads);
-  const long Ns = (static_cast<long>(N) + 127) / 128 * 128;    // dS scratch row pitch (keys)
-  CUtensorMap tmQ, tmDO, tmKV, tmDS;
+  CUtensorMap tmQ, tmDO, tmKV;
   int rc = make_tmap_bf16_2d(&tmQ, qn, 64, static_cast<uint64_t>(rows), 128, 64, 128);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmDO, d_o, 64, static_cast<uint64_t>(rows), 128, 64, 128);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmKV, kvn, 128, static_cast<uint64_t>(B) * N, 256, 64, 128);
   if (rc) return rc;
-  rc = make_tmap_bf16_3d(&tmDS, ds_scratch, static_cast<uint64_t>(Ns), static_cast<uint64_t>(R), static_cast<uint64_t>(B),
-                         static_cast<uint64_t>(Ns) * 2, static_cast<uint64_t>(Ns) * 2 * R, 64, 128);
-  if (rc) return rc;
+  const int n_row_tiles = static_cast<int>((R + kBtBQ - 1) / kBtBQ);
+  const int n_key_tiles = (N + kBtBK - 1) / kBtBK;
+  // chunk length T: as long as the per-CTA diagonal table (heads x (ceil(128 T / heads) + 128) floats) fits in shared
+  // memory, and long enough that the grid is at most ~4 CTAs per SM (each CTA pays a K/V load and a dK/dV flush)
+  auto wacc_of = [&](int T) { int w = (T * kBtBQ + heads - 1) / heads + 128; return w | 1; };
+  auto smem_of = [&](int T) { return kBoBias + (2 * heads * W + heads * wacc_of(T)) * 4 + 1024; };
+  auto units_of = [&](int T) {
+    long units = 0;
+    for (int kt = 0; kt < n_key_tiles; ++kt) {
+      const int first = (kt * kBtBK * heads) / kBtBQ;
+      units += (n_row_tiles - first + T - 1) / T;
+    }
+    return units;
+  };
+  OMLM_CHECK_ARG(smem_of(1) <= kBtMaxSmem, "attn_bwd_tc: too many heads (%d) for the shared-memory bias slices", heads);
+  int tiles_per_chunk = 1;
+  for (int cand = 2; cand <= 2 * n_row_tiles; cand *= 2) {
+    const int T = cand < n_row_tiles ? cand : n_row_tiles;
+    if (smem_of(T) > kBtMaxSmem) break;
+    tiles_per_chunk = T;
+    if ((T >= 4 && units_of(T) * B <= 4L * num_sms()) || T == n_row_tiles) break;
+  }
+  const int Wacc = wacc_of(tiles_per_chunk);
+  const int smem_bytes = smem_of(tiles_per_chunk);
   static int configured = 0;
   if (configured < smem_bytes) {
     OMLM_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = smem_bytes;
   }
-  const int n_row_tiles = static_cast<int>((R + kBtBQ - 1) / kBtBQ);
-  const int n_key_tiles = (N + kBtBK - 1) / kBtBK;
-  int tiles_per_chunk = n_row_tiles;
-  for (int cand = 4; cand <= n_row_tiles; cand *= 2) {
-    long units = 0;
-    for (int kt = 0; kt < n_key_tiles; ++kt) {
-      const int first = (kt * kBtBK * heads) / kBtBQ;
-      units += (n_row_tiles - first + cand - 1) / cand;
-    }
-    if (units * B <= 4L * num_sms()) { tiles_per_chunk = cand; break; }
-  }
-  int units_per_batch = 0;
-  for (int kt = 0; kt < n_key_tiles; ++kt) {
-    const int first = (kt * kBtBK * heads) / kBtBQ;
-    units_per_batch += (n_row_tiles - first + tiles_per_chunk - 1) / tiles_per_chunk;
-  }
+  const int units_per_batch = static_cast<int>(units_of(tiles_per_chunk));
   attn_bwd_tc_kernel<<<B * units_per_batch, kBtThreads, smem_bytes, st>>>(
-      tmQ, tmDO, tmKV, tmDS, lse2, dsum_scratch, table, table_ld, key_mask, dqn, dkvn, N, heads, scale, W, Wd,
+      tmQ, tmDO, tmKV, lse2, dsum_scratch, table, table_ld, key_mask, dqn, dkvn, dtable, N, heads, scale, W, Wd, Wacc,
       tiles_per_chunk, units_per_batch);
-  OMLM_LAUNCH_CHECK();
-  const int ichunk = 64;
-  const int n_ichunks = (N + ichunk - 1) / ichunk;
-  dim3 grid((N + 255) / 256, heads, B * n_ichunks);
-  attn_dbias_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(ds_scratch), Ns, Ns * R, dtable, table_ld, N,
-                                          heads, ichunk, n_ichunks);
   OMLM_LAUNCH_CHECK();
   return 0;
 }

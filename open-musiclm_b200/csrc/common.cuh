@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -60,6 +61,31 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
 }
 __device__ __forceinline__ float bf16_round(float x) {
   return __bfloat162float(__float2bfloat16_rn(x));
+}
+// ---- 16-bit operand formats -------------------------------------------------------------------
+// The tensor-core operands are 16-bit in two flavours (tcgen05 kind::f16 takes either, per operand, at the same rate):
+//   fp16 (11-bit significand) for tensors that are bounded by construction -- LayerNorm outputs, weights, and the
+//        FFN activations derived from them -- where it cuts the operand rounding error 8x against bf16;
+//   bf16 (8-bit significand, fp32 range) for everything whose range is not bounded: gradients, the raw residual
+//        stream feeding K/V, attention operands.
+// fp16 conversions saturate (F2FP.SATFINITE) instead of producing inf.
+enum : int { kFmtBF16 = 0, kFmtF32 = 1, kFmtF16 = 2 };
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
+  __half2 t = *reinterpret_cast<__half2*>(&v);
+  return __half22float2(t);
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {
+  if constexpr (F16) return pack_f16x2(lo, hi); else return pack_bf16x2(lo, hi);
+}
+template <bool F16>
+__device__ __forceinline__ float2 unpack16x2(uint32_t v) {
+  if constexpr (F16) return unpack_f16x2(v); else return unpack_bf16x2(v);
 }
 
 // ---- GELU (exact erf) ------------------------------------------------------------------------

@@ -16,19 +16,22 @@ namespace omlm {
 // [128 value columns | 128 gate columns] so that one 256-wide GEMM tile holds both halves of its channels.
 __device__ __forceinline__ int ileave(int c) { return ((c >> 7) << 8) + (c & 127); }
 
+// F16 selects the storage format of the forward activations u / h / hn (fp16 or bf16); gradients are always bf16.
+template <bool F16 = false>
 __device__ __forceinline__ void load8(const __nv_bfloat16* p, bool ok, float (&f)[8]) {
   uint4 raw = make_uint4(0, 0, 0, 0);
   if (ok) raw = *reinterpret_cast<const uint4*>(p);
   float2 t;
-  t = unpack_bf16x2(raw.x); f[0] = t.x; f[1] = t.y;
-  t = unpack_bf16x2(raw.y); f[2] = t.x; f[3] = t.y;
-  t = unpack_bf16x2(raw.z); f[4] = t.x; f[5] = t.y;
-  t = unpack_bf16x2(raw.w); f[6] = t.x; f[7] = t.y;
+  t = unpack16x2<F16>(raw.x); f[0] = t.x; f[1] = t.y;
+  t = unpack16x2<F16>(raw.y); f[2] = t.x; f[3] = t.y;
+  t = unpack16x2<F16>(raw.z); f[4] = t.x; f[5] = t.y;
+  t = unpack16x2<F16>(raw.w); f[6] = t.x; f[7] = t.y;
 }
+template <bool F16 = false>
 __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
   uint4 o;
-  o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-  o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+  o.x = pack16x2<F16>(f[0], f[1]); o.y = pack16x2<F16>(f[2], f[3]);
+  o.z = pack16x2<F16>(f[4], f[5]); o.w = pack16x2<F16>(f[6], f[7]);
   *reinterpret_cast<uint4*>(p) = o;
 }
 
@@ -64,9 +67,10 @@ __device__ __forceinline__ void load4(const __nv_bfloat16* p, bool ok, float (&f
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(256)
 ffn_norm_fwd_kernel(const __nv_bfloat16* __restrict__ h, const float2* __restrict__ rowsum,
-                    const float* __restrict__ gamma, __nv_bfloat16* __restrict__ hn, float2* __restrict__ stats,
+                    const float* __restrict__ gamma, __nv_bfloat16* __restrict__ hn, __nv_bfloat16* __restrict__ hn_copy, float2* __restrict__ stats,
                     uint8_t* __restrict__ keep_bits, long M, int F, int Fp, float drop_p,
                     const unsigned long long* __restrict__ seed_ptr, uint32_t layer) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -86,7 +90,7 @@ ffn_norm_fwd_kernel(const __nv_bfloat16* __restrict__ h, const float2* __restric
   const unsigned long long seed = (drop_p > 0.f) ? *seed_ptr : 0ull;
   for (int chunk = lane; chunk * 8 < Fp; chunk += 32) {
     float v[8];
-    load8(h + row * Fp + chunk * 8, true, v);
+    load8<F16>(h + row * Fp + chunk * 8, true, v);
     const float4 g0 = *reinterpret_cast<const float4*>(gamma + chunk * 8);
     const float4 g1 = *reinterpret_cast<const float4*>(gamma + chunk * 8 + 4);
     const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
@@ -98,7 +102,8 @@ ffn_norm_fwd_kernel(const __nv_bfloat16* __restrict__ h, const float2* __restric
       o[i] = (v[i] - mean) * rstd * gm[i];          // gamma is zero in the padding -> padded channels stay 0
       if (drop_p > 0.f) o[i] = keep[i] ? o[i] * keep_scale : 0.f;
     }
-    store8(hn + row * Fp + chunk * 8, o);
+    store8<F16>(hn + row * Fp + chunk * 8, o);
+    if (hn_copy != nullptr) store8<false>(hn_copy + row * Fp + chunk * 8, o);   // bf16 copy for the backward GEMMs
     if (drop_p > 0.f) {   // the backward pass reads the mask back (1 bit per element) instead of replaying Philox
       uint32_t bits = 0;
 #pragma unroll
@@ -172,6 +177,7 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(n) : "memory");
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(kTileThreads, 2)
 ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, const float2* __restrict__ stats,
                         const float2* __restrict__ rowstat, __nv_bfloat16* __restrict__ du,
@@ -246,8 +252,8 @@ ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, 
     const uint2 q2 = *reinterpret_cast<const uint2*>(su + ts * 512 + 256 + lane * 8);
     const uint2 p1 = *reinterpret_cast<const uint2*>(su + (ts + 1) * 512 + lane * 8);
     const uint2 q1 = *reinterpret_cast<const uint2*>(su + (ts + 1) * 512 + 256 + lane * 8);
-    ua2[0] = unpack_bf16x2(p2.x); ua2[1] = unpack_bf16x2(p2.y); ug2[0] = unpack_bf16x2(q2.x); ug2[1] = unpack_bf16x2(q2.y);
-    ua1[0] = unpack_bf16x2(p1.x); ua1[1] = unpack_bf16x2(p1.y); ug1[0] = unpack_bf16x2(q1.x); ug1[1] = unpack_bf16x2(q1.y);
+    ua2[0] = unpack16x2<F16>(p2.x); ua2[1] = unpack16x2<F16>(p2.y); ug2[0] = unpack16x2<F16>(q2.x); ug2[1] = unpack16x2<F16>(q2.y);
+    ua1[0] = unpack16x2<F16>(p1.x); ua1[1] = unpack16x2<F16>(p1.y); ug1[0] = unpack16x2<F16>(q1.x); ug1[1] = unpack16x2<F16>(q1.y);
   }
   const float2 z2 = make_float2(0.f, 0.f);
   float2 da2[2] = {z2, z2}, da1[2] = {z2, z2}, dg2[2] = {z2, z2}, dg1[2] = {z2, z2};
@@ -265,7 +271,7 @@ ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, 
     {
       const uint2 p = *reinterpret_cast<const uint2*>(su + (tl + 2) * 512 + lane * 8);
       const uint2 q = *reinterpret_cast<const uint2*>(su + (tl + 2) * 512 + 256 + lane * 8);
-      ua0[0] = unpack_bf16x2(p.x); ua0[1] = unpack_bf16x2(p.y); ug0[0] = unpack_bf16x2(q.x); ug0[1] = unpack_bf16x2(q.y);
+      ua0[0] = unpack16x2<F16>(p.x); ua0[1] = unpack16x2<F16>(p.y); ug0[0] = unpack16x2<F16>(q.x); ug0[1] = unpack16x2<F16>(q.y);
     }
     if (valid) {
       const uint2 dr = *reinterpret_cast<const uint2*>(sd + tl * 256 + lane * 8);
@@ -343,15 +349,18 @@ ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, 
 
 extern "C" {
 
-int omlm_ffn_norm_fwd(const void* h, const float* rowsum, const float* gamma, void* hn, float* stats, void* keep_bits,
-                      long M, int F, int Fp, float drop_p, const unsigned long long* seed, int layer, void* stream) {
+int omlm_ffn_norm_fwd(const void* h, const float* rowsum, const float* gamma, void* hn, void* hn_copy_bf16, float* stats,
+                      void* keep_bits, long M, int F, int Fp, float drop_p, const unsigned long long* seed, int layer,
+                      int act_f16, void* stream) {
   using namespace omlm;
   OMLM_CHECK_ARG(M > 0 && F > 0 && Fp >= F && Fp % 128 == 0, "ffn_norm_fwd: bad shape F=%d Fp=%d", F, Fp);
   OMLM_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || (seed != nullptr && keep_bits != nullptr)),
                  "ffn_norm_fwd: dropout needs a seed and a keep_bits buffer");
-  ffn_norm_fwd_kernel<<<static_cast<int>((M + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  auto kern = act_f16 ? ffn_norm_fwd_kernel<true> : ffn_norm_fwd_kernel<false>;
+  kern<<<static_cast<int>((M + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(h), reinterpret_cast<const float2*>(rowsum), gamma,
-      reinterpret_cast<__nv_bfloat16*>(hn), reinterpret_cast<float2*>(stats), reinterpret_cast<uint8_t*>(keep_bits), M, F, Fp,
+      reinterpret_cast<__nv_bfloat16*>(hn), reinterpret_cast<__nv_bfloat16*>(hn_copy_bf16), reinterpret_cast<float2*>(stats),
+      reinterpret_cast<uint8_t*>(keep_bits), M, F, Fp,
       drop_p, seed, static_cast<uint32_t>(layer));
   OMLM_LAUNCH_CHECK();
   return 0;
@@ -359,24 +368,27 @@ int omlm_ffn_norm_fwd(const void* h, const float* rowsum, const float* gamma, vo
 
 int omlm_ffn_mid_bwd(const void* dhn, const void* hn, const void* u, const float* stats, const float* conv_w,
                      const float* gamma, const void* keep_bits, float* rowstat_scratch, void* du, float* dgamma,
-                     float* dconv_w, int B, int N, int F, int Fp, float drop_p, void* stream) {
+                     float* dconv_w, int B, int N, int F, int Fp, float drop_p, int act_f16, void* stream) {
   using namespace omlm;
   OMLM_CHECK_ARG(B > 0 && N > 0 && F > 0 && Fp >= F && Fp % 128 == 0, "ffn_mid_bwd: bad shape F=%d Fp=%d", F, Fp);
   OMLM_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || keep_bits != nullptr), "ffn_mid_bwd: dropout needs keep_bits");
   auto st = reinterpret_cast<cudaStream_t>(stream);
   MidArgs a{reinterpret_cast<const __nv_bfloat16*>(u), conv_w, gamma, N, F, Fp, drop_p, reinterpret_cast<const uint8_t*>(keep_bits)};
   const long M = static_cast<long>(B) * N;
-  ffn_mid_bwd_stats_kernel<<<static_cast<int>((M + 7) / 8), 256, 0, st>>>(
+  auto stats_kern = ffn_mid_bwd_stats_kernel;
+  auto walk_kern = act_f16 ? ffn_mid_bwd_walk_kernel<true> : ffn_mid_bwd_walk_kernel<false>;
+  stats_kern<<<static_cast<int>((M + 7) / 8), 256, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(dhn), reinterpret_cast<const __nv_bfloat16*>(hn), gamma,
       reinterpret_cast<float2*>(rowstat_scratch), M, F, Fp, drop_p, a.keep_bits);
   OMLM_LAUNCH_CHECK();
   static bool configured = false;
   if (!configured) {
-    OMLM_CUDA(cudaFuncSetAttribute(ffn_mid_bwd_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem));
+    OMLM_CUDA(cudaFuncSetAttribute(ffn_mid_bwd_walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem));
+    OMLM_CUDA(cudaFuncSetAttribute(ffn_mid_bwd_walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem));
     configured = true;
   }
   dim3 grid(B * ((N + kTileRows - 1) / kTileRows), Fp / 128);
-  ffn_mid_bwd_walk_kernel<<<grid, kTileThreads, kTileSmem, st>>>(a, reinterpret_cast<const __nv_bfloat16*>(dhn),
+  walk_kern<<<grid, kTileThreads, kTileSmem, st>>>(a, reinterpret_cast<const __nv_bfloat16*>(dhn),
                                                                 reinterpret_cast<const float2*>(stats),
                                                                 reinterpret_cast<const float2*>(rowstat_scratch),
                                                                 reinterpret_cast<__nv_bfloat16*>(du), dgamma, dconv_w);

@@ -26,6 +26,9 @@ constexpr int kFuOffBar = kFuOffU + kFuBM * kFuUPitch;
 constexpr int kFuSmem = kFuOffBar + 256 + 1024;
 constexpr int kFuThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter / per SM sub-partition)
 
+// F16: xn, W1 arrive as fp16 and u, h leave as fp16 (all bounded by construction: LayerNorm output x weights);
+// otherwise everything is bf16.
+template <bool F16>
 __global__ void __launch_bounds__(kFuThreads, 1)
 gemm_ffn_up_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    __nv_bfloat16* __restrict__ u_out, __nv_bfloat16* __restrict__ h_out, float* __restrict__ rowsum,
@@ -77,7 +80,7 @@ gemm_ffn_up_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0) {   // ---------------------------------------------------------------- MMA issuer
-      constexpr uint32_t idesc = make_idesc_bf16(kFuBM, kFuBN, 0, 0);
+      constexpr uint32_t idesc = make_idesc_bf16(kFuBM, kFuBN, 0, 0) & (F16 ? ~((7u << 7) | (7u << 10)) : ~0u);
       int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
       for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -140,10 +143,10 @@ gemm_ffn_up_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint4 q;
-          q.x = pack_bf16x2(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1]));
-          q.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
-          q.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
-          q.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+          q.x = pack16x2<F16>(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1]));
+          q.y = pack16x2<F16>(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+          q.z = pack16x2<F16>(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+          q.w = pack16x2<F16>(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
           *reinterpret_cast<uint4*>(urow + half * 256 + c * 64 + j * 16) = q;
         }
       }
@@ -166,12 +169,12 @@ gemm_ffn_up_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         {
           const uint2 a = *reinterpret_cast<const uint2*>(rp - kFuUPitch + lane * 8);
           const uint2 g = *reinterpret_cast<const uint2*>(rp - kFuUPitch + 256 + lane * 8);
-          xv1[0] = unpack_bf16x2(a.x); xv1[1] = unpack_bf16x2(a.y); xg1[0] = unpack_bf16x2(g.x); xg1[1] = unpack_bf16x2(g.y);
+          xv1[0] = unpack16x2<F16>(a.x); xv1[1] = unpack16x2<F16>(a.y); xg1[0] = unpack16x2<F16>(g.x); xg1[1] = unpack16x2<F16>(g.y);
         }
         {
           const uint2 a = *reinterpret_cast<const uint2*>(rp - 2 * kFuUPitch + lane * 8);
           const uint2 g = *reinterpret_cast<const uint2*>(rp - 2 * kFuUPitch + 256 + lane * 8);
-          xv2[0] = unpack_bf16x2(a.x); xv2[1] = unpack_bf16x2(a.y); xg2[0] = unpack_bf16x2(g.x); xg2[1] = unpack_bf16x2(g.y);
+          xv2[0] = unpack16x2<F16>(a.x); xv2[1] = unpack16x2<F16>(a.y); xg2[0] = unpack16x2<F16>(g.x); xg2[1] = unpack16x2<F16>(g.y);
         }
         if (pos == 1) { xv2[0] = xv2[1] = xg2[0] = xg2[1] = make_float2(0.f, 0.f); }   // row t-2 belongs to the previous sequence
         float st[32];
@@ -185,7 +188,7 @@ gemm_ffn_up_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             *reinterpret_cast<uint4*>(ug + static_cast<long>(r) * (2L * Fp)) = *reinterpret_cast<const uint4*>(rr + lane * 16);
             const uint2 a = *reinterpret_cast<const uint2*>(rr + lane * 8);
             const uint2 g = *reinterpret_cast<const uint2*>(rr + 256 + lane * 8);
-            const float2 xv0[2] = {unpack_bf16x2(a.x), unpack_bf16x2(a.y)}, xg0[2] = {unpack_bf16x2(g.x), unpack_bf16x2(g.y)};
+            const float2 xv0[2] = {unpack16x2<F16>(a.x), unpack16x2<F16>(a.y)}, xg0[2] = {unpack16x2<F16>(g.x), unpack16x2<F16>(g.y)};
             if (pos == 0) {   // sequence start: no history (the zeros then slide into the t-2 slot for the next row)
               const float2 z = make_float2(0.f, 0.f);
               xv1[0] = xv1[1] = xg1[0] = xg1[1] = z;
@@ -203,7 +206,7 @@ gemm_ffn_up_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               xg2[q] = xg1[q]; xg1[q] = xg0[q];
             }
             s1 = sm.x + sm.y; s2 = sq.x + sq.y;
-            *reinterpret_cast<uint2*>(hg + static_cast<long>(r) * Fp) = make_uint2(pack_bf16x2(h[0].x, h[0].y), pack_bf16x2(h[1].x, h[1].y));
+            *reinterpret_cast<uint2*>(hg + static_cast<long>(r) * Fp) = make_uint2(pack16x2<F16>(h[0].x, h[0].y), pack16x2<F16>(h[1].x, h[1].y));
             if (++pos == Nseq) pos = 0;
           }
           st[2 * r] = s1;
@@ -238,7 +241,7 @@ gemm_ffn_up_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 }  // namespace omlm
 
 extern "C" int omlm_gemm_ffn_up(const void* xn, const void* w1_packed, const float* conv_w_packed, void* u_out, void* h_out,
-                                float* rowsum, int M, int Nseq, int K, int Fp, int max_ctas, void* stream) {
+                                float* rowsum, int M, int Nseq, int K, int Fp, int act_f16, int max_ctas, void* stream) {
   using namespace omlm;
   OMLM_CHECK_ARG(M > 0 && Nseq > 0 && K > 0 && K % 8 == 0 && Fp > 0 && Fp % 128 == 0, "gemm_ffn_up: bad shape M=%d K=%d Fp=%d", M, K, Fp);
   CUtensorMap tmA, tmB;
@@ -248,14 +251,16 @@ extern "C" int omlm_gemm_ffn_up(const void* xn, const void* w1_packed, const flo
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
-    OMLM_CUDA(cudaFuncSetAttribute(gemm_ffn_up_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmem));
+    OMLM_CUDA(cudaFuncSetAttribute(gemm_ffn_up_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmem));
+    OMLM_CUDA(cudaFuncSetAttribute(gemm_ffn_up_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmem));
     configured = true;
   }
   const int m_tiles = (M + kFuRowsOut - 1) / kFuRowsOut, n_tiles = (2 * Fp) / kFuBN;
   int grid = num_sms();
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
   if (m_tiles * n_tiles < grid) grid = m_tiles * n_tiles;
-  gemm_ffn_up_kernel<<<grid, kFuThreads, kFuSmem, reinterpret_cast<cudaStream_t>(stream)>>>(
+  auto kern = act_f16 ? gemm_ffn_up_kernel<true> : gemm_ffn_up_kernel<false>;
+  kern<<<grid, kFuThreads, kFuSmem, reinterpret_cast<cudaStream_t>(stream)>>>(
       tmA, tmB, reinterpret_cast<__nv_bfloat16*>(u_out), reinterpret_cast<__nv_bfloat16*>(h_out), rowsum, conv_w_packed, M,
       Nseq, K, Fp);
   OMLM_LAUNCH_CHECK();

@@ -48,7 +48,7 @@ struct GemmSmem {
 template <int BN, int A_MN, int B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const EpiParams ep, const int M, const int N, const int K, const int splits) {
+                 const EpiParams ep, const int M, const int N, const int K, const int splits, const uint32_t idesc) {
   using S = GemmSmem<BN>;
   constexpr int kStages = S::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -130,7 +130,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -295,7 +294,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 template <int BN, int A_MN, int B_MN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams& ep, int M,
-                       int N, int K, int splits, int max_ctas, cudaStream_t stream) {
+                       int N, int K, int splits, int max_ctas, int a_f16, int b_f16, cudaStream_t stream) {
   using S = GemmSmem<BN>;
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
   const int smem_bytes = S::kStages * S::kStageBytes + 1024 + 256;
@@ -309,23 +308,28 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Epi
   int grid = num_sms();
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
   if (work < grid) grid = work;
-  kern<<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmB, ep, M, N, K, splits);
+  // operand formats are instruction-descriptor bits (a_format @7, b_format @10: 0 = fp16, 1 = bf16), set per launch
+  uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+  if (a_f16) idesc &= ~(7u << 7);
+  if (b_f16) idesc &= ~(7u << 10);
+  kern<<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmB, ep, M, N, K, splits, idesc);
   OMLM_LAUNCH_CHECK();
   return 0;
 }
 
 }  // namespace omlm
 
-extern "C" int omlm_gemm_bf16(const void* A, int a_mn_major, long lda, const void* B, int b_mn_major,
-                              long ldb, int M, int N, int K, void* out, int out_f32, long ldo,
-                              const float* addend, long ldadd, float alpha, int splits,
-                              int row_split, int row_valid, int n_valid, int block_n, int max_ctas,
-                              void* stream_) {
+extern "C" int omlm_gemm16(const void* A, int a_f16, int a_mn_major, long lda, const void* B, int b_f16, int b_mn_major,
+                           long ldb, int M, int N, int K, void* out, int out_f32, long ldo,
+                           const float* addend, long ldadd, float alpha, int splits,
+                           int row_split, int row_valid, int n_valid, int block_n, int max_ctas,
+                           void* stream_) {
   using namespace omlm;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   OMLM_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem %d x %d x %d", M, N, K);
   OMLM_CHECK_ARG(block_n == 128 || block_n == 256, "gemm: block_n must be 128 or 256");
   OMLM_CHECK_ARG(splits >= 1, "gemm: splits must be >= 1");
+  OMLM_CHECK_ARG((a_f16 != 0) == (b_f16 != 0), "gemm: both operands must have the same 16-bit format (tcgen05 kind::f16 faults on fp16 x bf16)");
   OMLM_CHECK_ARG(splits == 1 || (out_f32 && addend == nullptr), "gemm: split-K needs fp32 atomic output and no addend");
   if (n_valid <= 0 || n_valid > N) n_valid = N;
   {  // every split must own at least one k-block (an empty split would publish an unwritten accumulator)
@@ -351,14 +355,23 @@ extern "C" int omlm_gemm_bf16(const void* A, int a_mn_major, long lda, const voi
   ep.row_split = row_split; ep.row_valid = row_valid; ep.n_valid = n_valid;
   const int key = (block_n == 256 ? 4 : 0) | (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
   switch (key) {
-    case 0: return launch_gemm<128, 0, 0>(tmA, tmB, ep, M, N, K, splits, max_ctas, stream);
-    case 1: return launch_gemm<128, 0, 1>(tmA, tmB, ep, M, N, K, splits, max_ctas, stream);
-    case 3: return launch_gemm<128, 1, 1>(tmA, tmB, ep, M, N, K, splits, max_ctas, stream);
-    case 4: return launch_gemm<256, 0, 0>(tmA, tmB, ep, M, N, K, splits, max_ctas, stream);
-    case 5: return launch_gemm<256, 0, 1>(tmA, tmB, ep, M, N, K, splits, max_ctas, stream);
-    case 7: return launch_gemm<256, 1, 1>(tmA, tmB, ep, M, N, K, splits, max_ctas, stream);
+    case 0: return launch_gemm<128, 0, 0>(tmA, tmB, ep, M, N, K, splits, max_ctas, a_f16, b_f16, stream);
+    case 1: return launch_gemm<128, 0, 1>(tmA, tmB, ep, M, N, K, splits, max_ctas, a_f16, b_f16, stream);
+    case 3: return launch_gemm<128, 1, 1>(tmA, tmB, ep, M, N, K, splits, max_ctas, a_f16, b_f16, stream);
+    case 4: return launch_gemm<256, 0, 0>(tmA, tmB, ep, M, N, K, splits, max_ctas, a_f16, b_f16, stream);
+    case 5: return launch_gemm<256, 0, 1>(tmA, tmB, ep, M, N, K, splits, max_ctas, a_f16, b_f16, stream);
+    case 7: return launch_gemm<256, 1, 1>(tmA, tmB, ep, M, N, K, splits, max_ctas, a_f16, b_f16, stream);
     default:
       set_last_error("gemm: operand majors (a_mn=%d, b_mn=%d) not instantiated", a_mn_major, b_mn_major);
       return 1;
   }
+}
+
+extern "C" int omlm_gemm_bf16(const void* A, int a_mn_major, long lda, const void* B, int b_mn_major,
+                              long ldb, int M, int N, int K, void* out, int out_f32, long ldo,
+                              const float* addend, long ldadd, float alpha, int splits,
+                              int row_split, int row_valid, int n_valid, int block_n, int max_ctas,
+                              void* stream_) {
+  return omlm_gemm16(A, 0, a_mn_major, lda, B, 0, b_mn_major, ldb, M, N, K, out, out_f32, ldo, addend, ldadd, alpha, splits,
+                     row_split, row_valid, n_valid, block_n, max_ctas, stream_);
 }

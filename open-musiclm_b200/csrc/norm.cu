@@ -12,13 +12,14 @@ namespace omlm {
 constexpr int kNormThreads = 256;  // 8 rows per block
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm forward: y = (x - mean) * rstd * gamma  -> bf16;  optional raw bf16 copy of x;
-// stats[m] = (mean, rstd).  NCHUNK * 128 >= D.
+// LayerNorm forward: y = (x - mean) * rstd * gamma  -> fp16 (y_f16) or bf16;  optional bf16 copy of y (the
+// backward GEMMs pair it with bf16 gradients: tcgen05 wants one format for both operands); optional raw bf16 copy
+// of x;  stats[m] = (mean, rstd).  NCHUNK * 128 >= D.  (|y| <= sqrt(D) * |gamma|: bounded, hence fp16-safe.)
 template <int NCHUNK>
 __global__ void __launch_bounds__(kNormThreads)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                     __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ xraw,
-                     float2* __restrict__ stats, const int* __restrict__ dest_row, int M, int D) {
+                     __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ ycopy, __nv_bfloat16* __restrict__ xraw,
+                     float2* __restrict__ stats, const int* __restrict__ dest_row, int M, int D, int y_f16) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (kNormThreads / 32) + warp;
   if (row >= M) return;
@@ -51,10 +52,16 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
     if (col < D) {
       if (orow >= 0) {
         const float4 g = *reinterpret_cast<const float4*>(gamma + col);
+        const float y0 = (v[c].x - mean) * rstd * g.x, y1 = (v[c].y - mean) * rstd * g.y;
+        const float y2 = (v[c].z - mean) * rstd * g.z, y3 = (v[c].w - mean) * rstd * g.w;
         uint2 o;
-        o.x = pack_bf16x2((v[c].x - mean) * rstd * g.x, (v[c].y - mean) * rstd * g.y);
-        o.y = pack_bf16x2((v[c].z - mean) * rstd * g.z, (v[c].w - mean) * rstd * g.w);
+        if (y_f16) { o.x = pack_f16x2(y0, y1); o.y = pack_f16x2(y2, y3); }
+        else       { o.x = pack_bf16x2(y0, y1); o.y = pack_bf16x2(y2, y3); }
         *reinterpret_cast<uint2*>(y + orow * D + col) = o;
+        if (ycopy != nullptr) {
+          o.x = pack_bf16x2(y0, y1); o.y = pack_bf16x2(y2, y3);
+          *reinterpret_cast<uint2*>(ycopy + orow * D + col) = o;
+        }
       }
       if (xraw != nullptr) {
         uint2 o;
@@ -351,11 +358,11 @@ qk_l2norm_bwd_kernel(const float* __restrict__ dqn, const float* __restrict__ dk
 }
 
 template <int NCHUNK>
-static int launch_ln_fwd(const float* x, const float* gamma, __nv_bfloat16* y, __nv_bfloat16* xraw,
-                         float2* stats, const int* dest_row, int M, int D, cudaStream_t st) {
+static int launch_ln_fwd(const float* x, const float* gamma, __nv_bfloat16* y, __nv_bfloat16* ycopy, __nv_bfloat16* xraw,
+                         float2* stats, const int* dest_row, int M, int D, int y_f16, cudaStream_t st) {
   const int rows_per_block = kNormThreads / 32;
   layernorm_fwd_kernel<NCHUNK><<<(M + rows_per_block - 1) / rows_per_block, kNormThreads, 0, st>>>(
-      x, gamma, y, xraw, stats, dest_row, M, D);
+      x, gamma, y, ycopy, xraw, stats, dest_row, M, D, y_f16);
   OMLM_LAUNCH_CHECK();
   return 0;
 }
@@ -387,20 +394,21 @@ static int launch_ln_bwd(const __nv_bfloat16* dy, const float* x, const float2* 
 
 extern "C" {
 
-int omlm_layernorm_fwd(const float* x, const float* gamma, void* y_bf16, void* xraw_bf16, float* stats,
-                       const int* dest_row, int M, int D, void* stream) {
+int omlm_layernorm_fwd(const float* x, const float* gamma, void* y_bf16, int y_f16, void* ycopy_bf16, void* xraw_bf16,
+                       float* stats, const int* dest_row, int M, int D, void* stream) {
   using namespace omlm;
   OMLM_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0 && D <= 2048, "layernorm_fwd: unsupported shape %d x %d", M, D);
   auto st = reinterpret_cast<cudaStream_t>(stream);
   auto y = reinterpret_cast<__nv_bfloat16*>(y_bf16);
   auto xr = reinterpret_cast<__nv_bfloat16*>(xraw_bf16);
+  auto yc = reinterpret_cast<__nv_bfloat16*>(ycopy_bf16);
   auto s2 = reinterpret_cast<float2*>(stats);
   const int nchunk = (D + 127) / 128;
-  if (nchunk <= 1) return launch_ln_fwd<1>(x, gamma, y, xr, s2, dest_row, M, D, st);
-  if (nchunk <= 2) return launch_ln_fwd<2>(x, gamma, y, xr, s2, dest_row, M, D, st);
-  if (nchunk <= 4) return launch_ln_fwd<4>(x, gamma, y, xr, s2, dest_row, M, D, st);
-  if (nchunk <= 8) return launch_ln_fwd<8>(x, gamma, y, xr, s2, dest_row, M, D, st);
-  return launch_ln_fwd<16>(x, gamma, y, xr, s2, dest_row, M, D, st);
+  if (nchunk <= 1) return launch_ln_fwd<1>(x, gamma, y, yc, xr, s2, dest_row, M, D, y_f16, st);
+  if (nchunk <= 2) return launch_ln_fwd<2>(x, gamma, y, yc, xr, s2, dest_row, M, D, y_f16, st);
+  if (nchunk <= 4) return launch_ln_fwd<4>(x, gamma, y, yc, xr, s2, dest_row, M, D, y_f16, st);
+  if (nchunk <= 8) return launch_ln_fwd<8>(x, gamma, y, yc, xr, s2, dest_row, M, D, y_f16, st);
+  return launch_ln_fwd<16>(x, gamma, y, yc, xr, s2, dest_row, M, D, y_f16, st);
 }
 
 int omlm_layernorm_bwd(const void* dy_bf16, const float* x, const float* stats, const float* gamma,

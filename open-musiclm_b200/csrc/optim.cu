@@ -6,6 +6,7 @@
 // so the decay rule is a single index compare.  Clip coefficient and hyper-parameters are read from
 // device memory: the step never synchronises with the host.
 #include "common.cuh"
+#include <type_traits>
 #include "../../include/omlm_b200.h"
 
 namespace omlm {
@@ -88,7 +89,8 @@ __device__ __forceinline__ void pack_quad(long i, const float* __restrict__ src,
   OutT* d = dst + r * dst_ld + c;
   if (vec_dst) {
     if constexpr (sizeof(OutT) == 2) {
-      uint2 o; o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+      constexpr bool kHalf = std::is_same<OutT, __half>::value;
+      uint2 o; o.x = pack16x2<kHalf>(v[0], v[1]); o.y = pack16x2<kHalf>(v[2], v[3]);
       *reinterpret_cast<uint2*>(d) = o;
     } else {
       *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
@@ -97,7 +99,9 @@ __device__ __forceinline__ void pack_quad(long i, const float* __restrict__ src,
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (c + j < cols_p) {
-        if constexpr (sizeof(OutT) == 2) d[j] = __float2bfloat16_rn(v[j]); else d[j] = v[j];
+        if constexpr (std::is_same<OutT, __half>::value) d[j] = __float2half_rn(fminf(fmaxf(v[j], -65504.f), 65504.f));
+        else if constexpr (sizeof(OutT) == 2) d[j] = __float2bfloat16_rn(v[j]);
+        else d[j] = v[j];
       }
     }
   }
@@ -113,8 +117,9 @@ __global__ void pack_kernel(const float* __restrict__ src, long src_ld, int rows
 
 // All repacks of one optimiser step in ONE launch: the job table lives in device memory, work is cut into units of
 // 256 quads and blocks stride over the concatenated unit list (45 small launches -> 1 bandwidth-bound pass).
+constexpr int kPackMaxJobs = 512;
 __global__ void __launch_bounds__(256) pack_multi_kernel(const omlm_pack_job* __restrict__ jobs, int njobs, long total_units) {
-  __shared__ long starts[65];
+  __shared__ long starts[kPackMaxJobs + 1];
   for (int j = threadIdx.x; j < njobs; j += blockDim.x) starts[j] = jobs[j].unit_start;
   if (threadIdx.x == 0) starts[njobs] = total_units;
   __syncthreads();
@@ -125,7 +130,8 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const omlm_pack_job* __
     const long i = (u - jb.unit_start) * 256 + threadIdx.x;
     const long total = static_cast<long>(jb.rows_p) * ((jb.cols_p + 3) >> 2);
     if (i >= total) continue;
-    if (jb.dst_f32) pack_quad<float>(i, jb.src, jb.src_ld, jb.rows_valid, jb.cols_valid, reinterpret_cast<float*>(jb.dst), jb.dst_ld, jb.cols_p, jb.split_dst, jb.split_src);
+    if (jb.dst_fmt == kFmtF32) pack_quad<float>(i, jb.src, jb.src_ld, jb.rows_valid, jb.cols_valid, reinterpret_cast<float*>(jb.dst), jb.dst_ld, jb.cols_p, jb.split_dst, jb.split_src);
+    else if (jb.dst_fmt == kFmtF16) pack_quad<__half>(i, jb.src, jb.src_ld, jb.rows_valid, jb.cols_valid, reinterpret_cast<__half*>(jb.dst), jb.dst_ld, jb.cols_p, jb.split_dst, jb.split_src);
     else pack_quad<__nv_bfloat16>(i, jb.src, jb.src_ld, jb.rows_valid, jb.cols_valid, reinterpret_cast<__nv_bfloat16*>(jb.dst), jb.dst_ld, jb.cols_p, jb.split_dst, jb.split_src);
   }
 }
@@ -168,15 +174,18 @@ int omlm_adamw_step(float* p, const float* g, float* m, float* v, long n, long n
   return 0;
 }
 
-int omlm_pack(const float* src, long src_ld, int rows_valid, int cols_valid, void* dst, int dst_f32, long dst_ld,
+int omlm_pack(const float* src, long src_ld, int rows_valid, int cols_valid, void* dst, int dst_fmt, long dst_ld,
               int rows_p, int cols_p, int split_dst, int split_src, void* stream) {
   using namespace omlm;
   OMLM_CHECK_ARG(rows_p > 0 && cols_p > 0, "pack: empty");
   const long total = static_cast<long>(rows_p) * ((cols_p + 3) / 4);
   const int blocks = static_cast<int>(std::min<long>((total + 255) / 256, static_cast<long>(num_sms()) * 16));
   auto st = reinterpret_cast<cudaStream_t>(stream);
-  if (dst_f32)
+  OMLM_CHECK_ARG(dst_fmt == kFmtBF16 || dst_fmt == kFmtF32 || dst_fmt == kFmtF16, "pack: dst_fmt must be 0 (bf16), 1 (fp32) or 2 (fp16)");
+  if (dst_fmt == kFmtF32)
     pack_kernel<float><<<blocks, 256, 0, st>>>(src, src_ld, rows_valid, cols_valid, reinterpret_cast<float*>(dst), dst_ld, rows_p, cols_p, split_dst, split_src);
+  else if (dst_fmt == kFmtF16)
+    pack_kernel<__half><<<blocks, 256, 0, st>>>(src, src_ld, rows_valid, cols_valid, reinterpret_cast<__half*>(dst), dst_ld, rows_p, cols_p, split_dst, split_src);
   else
     pack_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(src, src_ld, rows_valid, cols_valid, reinterpret_cast<__nv_bfloat16*>(dst), dst_ld, rows_p, cols_p, split_dst, split_src);
   OMLM_LAUNCH_CHECK();
@@ -185,7 +194,7 @@ int omlm_pack(const float* src, long src_ld, int rows_valid, int cols_valid, voi
 
 int omlm_pack_multi(const omlm_pack_job* jobs_device, int njobs, long total_units, void* stream) {
   using namespace omlm;
-  OMLM_CHECK_ARG(jobs_device != nullptr && njobs > 0 && njobs <= 64 && total_units > 0, "pack_multi: need 1..64 jobs");
+  OMLM_CHECK_ARG(jobs_device != nullptr && njobs > 0 && njobs <= kPackMaxJobs && total_units > 0, "pack_multi: need 1..%d jobs per table (got %d)", kPackMaxJobs, njobs);
   const int blocks = static_cast<int>(std::min<long>(total_units, static_cast<long>(num_sms()) * 16));
   pack_multi_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(jobs_device, njobs, total_units);
   OMLM_LAUNCH_CHECK();

@@ -28,7 +28,7 @@ __global__ void token_plan_kernel(const TokenPlanArgs a, const unsigned char* __
                                   const unsigned char* __restrict__ forget_keep,
                                   long long* __restrict__ ids_out, int* __restrict__ src_row,
                                   unsigned char* __restrict__ key_mask, int* __restrict__ labels,
-                                  int N, int n_ids_total, int n_labels_total) {
+                                  int* __restrict__ err_flag, int N, int n_ids_total, int n_labels_total) {
   const int b = blockIdx.x;
   int pos = 0, id_off = 0, lab_off = 0;
   for (int s = 0; s < a.n_seqs; ++s) {
@@ -63,7 +63,11 @@ __global__ void token_plan_kernel(const TokenPlanArgs a, const unsigned char* __
       if (a.nq[s] > 1) c += static_cast<long long>(a.codebook[s]) * (t % a.nq[s]);  // :126-130
       const bool pad = (c == a.pad_id);                                               // utils.py:133
       const int p = pos + 1 + t;
-      src_row[static_cast<long long>(b) * N + p] = pad ? -1 : a.emb_row_base[s] + static_cast<int>(c);
+      // nn.Embedding raises on an index outside [0, (codebook+1) * q): here the row is dropped (zero embedding, no
+      // out-of-bounds read) and the error is latched in err_flag for the host to raise at its next synchronisation
+      const bool oob = !pad && (c < 0 || c >= (static_cast<long long>(a.codebook[s]) + 1) * a.nq[s]);
+      if (oob && err_flag != nullptr) atomicOr(err_flag, 1 << s);
+      src_row[static_cast<long long>(b) * N + p] = (pad || oob) ? -1 : a.emb_row_base[s] + static_cast<int>(c);
       if (mask_in != nullptr) m = mask_in[static_cast<long long>(b) * N + p];
       if (forget_keep != nullptr) m = m && forget_keep[static_cast<long long>(b) * N + p];
       key_mask[static_cast<long long>(b) * N + p] = m;
@@ -144,7 +148,7 @@ int omlm_token_plan(int n_seqs, const long long* const* ids, const int* len, con
                     int append_eos, int drop_last, int mask_cond, int pad_id,
                     const unsigned char* mask_in, const unsigned char* forget_keep,
                     long long* ids_out, int* src_row, unsigned char* key_mask, int* labels,
-                    void* stream) {
+                    int* err_flag, void* stream) {
   using namespace omlm;
   OMLM_CHECK_ARG(n_seqs >= 1 && n_seqs <= OMLM_MAX_SEQS, "token_plan: n_seqs %d out of range", n_seqs);
   OMLM_CHECK_ARG(B > 0, "token_plan: empty batch");
@@ -161,7 +165,7 @@ int omlm_token_plan(int n_seqs, const long long* const* ids, const int* len, con
     N += 1 + n_tok; n_ids += n_tok; n_lab += n_with_eos;
   }
   token_plan_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      a, mask_in, forget_keep, ids_out, src_row, key_mask, labels, N, n_ids, n_lab);
+      a, mask_in, forget_keep, ids_out, src_row, key_mask, labels, err_flag, N, n_ids, n_lab);
   OMLM_LAUNCH_CHECK();
   return 0;
 }

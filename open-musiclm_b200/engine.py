@@ -8,12 +8,22 @@ HBM layout
         [embeddings | logit heads | layer matrices | rel-pos MLP matrices]   <- weight-decayed (ndim >= 2)
         [start tokens | gammas, scales, MLP biases]                          <- not decayed
         every nn.Parameter of the module is a view into arena_p (and its .grad into arena_g).
-  packed weights (bf16, refreshed after every parameter update):
+  packed weights (16-bit, refreshed after every parameter update):
         wq [h*64, d], wkv [128, d], wo [d, h*64], w1 [2*Fp, d] (value rows | gate rows, zero padded),
         w2 [d, Fp], logit heads [q, Cp, d];  conv taps fp32 [2*Fp, 3], inner gamma fp32 [Fp].
-  activations: residual stream fp32 [M, d]; GEMM operands bf16; attention statistics fp32.
+  activations: residual stream fp32 [M, d]; GEMM operands 16-bit; attention statistics fp32.
+
+16-bit operand formats (csrc/common.cuh): tcgen05 kind::f16 runs fp16 and bf16 at the same rate, but both operands
+of one MMA must share the format (fp16 x bf16 faults on B200 -- measured).  The FORWARD GEMMs whose operands are bounded
+by construction -- LayerNorm outputs (xn, xn2, hn, xf) against weights, and the FFN activations between them (u, h) --
+run in fp16 (11-bit significand: 8x less operand rounding than bf16; this is what keeps the logits within 1e-2 of the
+fp32 reference at 24 layers: 3.6e-3 instead of 1.25e-2).  Everything that touches an unbounded range stays bf16: every
+BACKWARD GEMM (gradients), the K/V projection of the raw residual stream, attention and its output projection.  So
+the weights are packed twice (fp16 for forward, bf16 for backward) and the saved LayerNorm outputs carry a bf16
+duplicate for the weight-gradient GEMMs.  OMLM_ACT16=bf16 switches the whole path back to bf16 (diagnostics only).
 """
 import math
+import os
 from typing import List, Optional
 
 import torch
@@ -89,6 +99,10 @@ class Engine:
         self.Cp = [_round_up(c, 64) for c in self.C]
         self.drop_p = float(module.ff_dropout)
         self.alpha = float(module.grad_shrink_alpha)
+        mode = os.environ.get("OMLM_ACT16", "fp16")
+        if mode not in ("fp16", "bf16"):
+            raise lib.OmlmError(f"OMLM_ACT16 must be 'fp16' or 'bf16', got {mode!r}")
+        self.a16 = torch.float16 if mode == "fp16" else torch.bfloat16     # bounded forward operands (see module doc)
         self._build_arena()
         self._alloc_packed()
         self._packed_version = None
@@ -98,6 +112,7 @@ class Engine:
         self.step_count = 0
         self.adam_m = None
         self.adam_v = None
+        self.err_flag = torch.zeros(1, dtype=torch.int32, device=dev)  # latched by omlm_token_plan (token id out of range)
         self.loss_acc = torch.zeros(2, device=dev)
         self.sumsq = torch.zeros(1, device=dev, dtype=torch.float64)
 
@@ -149,18 +164,23 @@ class Engine:
         return sum(p._version for p in self._param_list)
 
     def _alloc_packed(self):
-        dev, bf = self.dev, torch.bfloat16
+        dev, bf, a16 = self.dev, torch.bfloat16, self.a16
         d, HD, Fp = self.d, self.HD, self.Fp
+        dual = a16 != bf        # forward operands in fp16, backward operands (suffix _b) in bf16; one buffer when equal
         self.pk = []
         for _ in range(self.L):
-            self.pk.append(dict(
-                wq=torch.empty(HD, d, device=dev, dtype=bf), wkv=torch.empty(128, d, device=dev, dtype=bf),
-                wo=torch.empty(d, HD, device=dev, dtype=bf), w1=torch.empty(2 * Fp, d, device=dev, dtype=bf),
-                w2=torch.empty(d, Fp, device=dev, dtype=bf), conv=torch.empty(2 * Fp, 3, device=dev),
-                gin=torch.empty(Fp, device=dev)))
-        self.pk_logit = [torch.empty(s.num_quantizers, cp, d, device=dev, dtype=bf) for s, cp in zip(self.seqs, self.Cp)]
+            pk = dict(
+                wq=torch.empty(HD, d, device=dev, dtype=a16), w1=torch.empty(2 * Fp, d, device=dev, dtype=a16),
+                w2=torch.empty(d, Fp, device=dev, dtype=a16),
+                wkv_b=torch.empty(128, d, device=dev, dtype=bf), wo_b=torch.empty(d, HD, device=dev, dtype=bf),
+                conv=torch.empty(2 * Fp, 3, device=dev), gin=torch.empty(Fp, device=dev))
+            for k in ("wq", "w1", "w2"):
+                pk[k + "_b"] = torch.empty_like(pk[k], dtype=bf) if dual else pk[k]
+            self.pk.append(pk)
+        self.pk_logit = [torch.empty(s.num_quantizers, cp, d, device=dev, dtype=a16) for s, cp in zip(self.seqs, self.Cp)]
+        self.pk_logit_b = [torch.empty_like(t, dtype=bf) if dual else t for t in self.pk_logit]
         self._pack_table = None
-        self.pk_rp = [torch.empty(self.Hr, 3 * self.Hr, device=dev, dtype=bf) for _ in range(2)]   # rel-pos MLP layers 1, 2: [hi|lo|hi]
+        self.pk_rp = [torch.empty(self.Hr, 3 * self.Hr, device=dev, dtype=torch.bfloat16) for _ in range(2)]   # rel-pos MLP layers 1, 2: [hi|lo|hi]
 
     def refresh_packed(self, force=False):
         ver = self.params_version()
@@ -172,22 +192,34 @@ class Engine:
             tab = lib.PackTable(self.dev)
             for l, pk in enumerate(self.pk):
                 p = f"transformer.layers.{l}."
-                tab.add(pv[p + "0.to_q.weight"], d, HD, d, pk["wq"], HD, d)
-                tab.add(pv[p + "0.to_kv.weight"], d, 128, d, pk["wkv"], 128, d)
-                tab.add(pv[p + "0.to_out.0.weight"], HD, d, HD, pk["wo"], d, HD)
-                tab.add(pv[p + "2.1.weight"], d, 2 * F, d, pk["w1"], 2 * Fp, d, split_dst=-1, split_src=F)
-                tab.add(pv[p + "2.6.weight"], F, d, F, pk["w2"], d, Fp)
+                for sfx in (("", "_b") if pk["wq"] is not pk["wq_b"] else ("",)):
+                    tab.add(pv[p + "0.to_q.weight"], d, HD, d, pk["wq" + sfx], HD, d)
+                    tab.add(pv[p + "2.1.weight"], d, 2 * F, d, pk["w1" + sfx], 2 * Fp, d, split_dst=-1, split_src=F)
+                    tab.add(pv[p + "2.6.weight"], F, d, F, pk["w2" + sfx], d, Fp)
+                tab.add(pv[p + "0.to_kv.weight"], d, 128, d, pk["wkv_b"], 128, d)
+                tab.add(pv[p + "0.to_out.0.weight"], HD, d, HD, pk["wo_b"], d, HD)
                 tab.add(pv[p + "2.2.ds_conv.weight"], 3, 2 * F, 3, pk["conv"], 2 * Fp, 3, split_dst=-1, split_src=F)
                 tab.add(pv[p + "2.4.gamma"], F, 1, F, pk["gin"], 1, Fp)
             for s, seq in enumerate(self.seqs):
                 # [q, C, d] -> [q, Cp, d]: every head padded with zero rows
-                tab.add(pv[f"logit_weights.{s}"], d, seq.num_quantizers * self.C[s], d, self.pk_logit[s].view(-1, d),
-                         seq.num_quantizers * self.Cp[s], d, split_dst=self.Cp[s], split_src=self.C[s])
+                for dst in ((self.pk_logit[s], self.pk_logit_b[s]) if self.pk_logit[s] is not self.pk_logit_b[s] else (self.pk_logit[s],)):
+                    tab.add(pv[f"logit_weights.{s}"], d, seq.num_quantizers * self.C[s], d, dst.view(-1, d),
+                            seq.num_quantizers * self.Cp[s], d, split_dst=self.Cp[s], split_src=self.C[s])
             self._pack_table = tab
         self._pack_table.run()
         for j in (1, 2):
             lib.split3_bf16(pv[f"transformer.rel_pos_bias.net.{j}.0.weight"], self.pk_rp[j - 1], weight_mode=True)
         self._packed_version = ver
+
+    def check_errors(self):
+        """Raises if a token id outside an embedding table was seen since the last check (nn.Embedding's IndexError;
+        asynchronous like the reference's device-side assert on CUDA: this call synchronises)."""
+        bits = int(self.err_flag.item())
+        if bits:
+            self.err_flag.zero_()
+            bad = [s for s in range(len(self.seqs)) if bits >> s & 1]
+            raise lib.OmlmError(f"token id out of range for the embedding table of sequence(s) {bad} "
+                                f"(valid ids: 0..codebook_size, or the pad id at quantizer-0 positions)")
 
     # ------------------------------------------------------------------------------------------ plans / workspaces
     def plan(self, B, n_tok) -> _Plan:
@@ -200,7 +232,7 @@ class Engine:
         key = (pl.B, tuple(pl.n_tok), train)
         if key in self._ws:
             return self._ws[key]
-        dev, bf, f32 = self.dev, torch.bfloat16, torch.float32
+        dev, bf, f32, a16 = self.dev, torch.bfloat16, torch.float32, self.a16
         M, d, HD, Fp, h = pl.M, self.d, self.HD, self.Fp, self.h
         E = lambda *shape, dt=bf: torch.empty(*shape, device=dev, dtype=dt)
         nl = self.L if train else 1
@@ -211,25 +243,28 @@ class Engine:
             qn=[E(M, HD) for _ in range(nl)], kvn=[E(M, 128) for _ in range(nl)],
             o=[E(M, HD) for _ in range(nl)], lse=[E(M * h, dt=f32) for _ in range(nl)],
             xn2=[E(M, d) for _ in range(nl)], st_f=[E(M, 2, dt=f32) for _ in range(nl)],
-            u=[E(M, 2 * Fp) for _ in range(nl)], hn=[E(M, Fp) for _ in range(nl)], st_i=[E(M, 2, dt=f32) for _ in range(nl)],
+            u=[E(M, 2 * Fp, dt=a16) for _ in range(nl)], hn=[E(M, Fp) for _ in range(nl)], st_i=[E(M, 2, dt=f32) for _ in range(nl)],
             keep=[E(M, Fp // 8, dt=torch.uint8) for _ in range(nl)],   # FFN dropout keep mask, 1 bit per element
-            xf=E(max(pl.rows_total, 1), d), st_o=E(M, 2, dt=f32), h=E(M, Fp), rowsum=E(M, Fp // 128, 2, dt=f32),
+            xf=E(max(pl.rows_total, 1), d), st_o=E(M, 2, dt=f32), h=E(M, Fp, dt=a16), rowsum=E(M, Fp // 128, 2, dt=f32),
             logits=[E(max(pl.B * c, 1), self.Cp[s], dt=f32) for (s, qi, c, b0) in pl.groups],
             # rel-pos MLP
             rp_in=E(pl.N, 1, dt=f32), rp_z=[E(pl.N, self.Hr, dt=f32) for _ in range(3)],
             rp_a=[E(pl.N, self.Hr, dt=f32) for _ in range(3)], table=E(h, pl.N, dt=f32),
             rp_a3=[E(pl.N, 3 * self.Hr) for _ in range(2)],
         )
+        if a16 != bf:   # fp16 forward operands (transient: one buffer each); xn / xn2 / hn / xf above are then the bf16
+            ws.update(xn16=E(M, d, dt=a16), xn2_16=E(M, d, dt=a16), hn16=E(M, Fp, dt=a16),   # duplicates kept for backward
+                      xf16=E(max(pl.rows_total, 1), d, dt=a16))
         lib.arange_f32(ws["rp_in"])
         if train:
             ws.update(
                 dlogits=[E(max(pl.B * c, 1), self.Cp[s]) for (s, qi, c, b0) in pl.groups],
                 dxf=E(max(pl.rows_total, 1), d), dx=[E(M, d, dt=f32) for _ in range(2)], dx_bf=E(M, d),
                 dhn=E(M, Fp), rowstat=E(M, 2, dt=f32), du=E(M, 2 * Fp), dxn=E(M, d), dxraw=E(M, d),
-                d_o=E(M, HD), ds=E(pl.B, pl.N * h, _round_up(pl.N, 128)), dqn=E(M, HD, dt=f32), dkvn=E(M, 128, dt=f32), dsum=E(M * h, dt=f32),
+                d_o=E(M, HD), dqn=E(M, HD, dt=f32), dkvn=E(M, 128, dt=f32), dsum=E(M * h, dt=f32),
                 dq_raw=E(M, HD), dkv_raw=E(M, 128), dtable=E(h, pl.N, dt=f32),
                 dgin=E(Fp, dt=f32), dconv=E(2 * Fp, 3, dt=f32),
-                rp_d0=E(pl.N, self.Hr, dt=f32), rp_d1=E(pl.N, self.Hr, dt=f32), rp_dz_bf=E(pl.N, self.Hr),
+                rp_d0=E(pl.N, self.Hr, dt=f32), rp_d1=E(pl.N, self.Hr, dt=f32), rp_dz3=E(pl.N, 3 * self.Hr),
             )
         self._ws[key] = ws
         return ws
@@ -280,28 +315,34 @@ class Engine:
         lib.embed_gather(self.table, src_row, x[0])
         self._relpos_table(ws, N)
         drop_p = self.drop_p if drop else 0.0
+        f16 = self.a16 != torch.bfloat16
+        dup = f16 and train            # the backward pass needs bf16 duplicates of the fp16 forward operands
         for l in range(self.L):
             i = l if train else 0
             xa, xm, xo = (x[2 * l], x[2 * l + 1], x[2 * l + 2]) if train else (x[0], x[1], x[0])
             p, pk = f"transformer.layers.{l}.", self.pk[l]
-            lib.layernorm_fwd(xa, pv[p + "0.norm.gamma"], ws["xn"][i], ws["xraw"][i], ws["st_a"][i])
-            lib.gemm(ws["xn"][i], pk["wq"], ws["q_raw"][i], block_n=self._bn_for(M, HD, d))
-            lib.gemm(ws["xraw"][i], pk["wkv"], ws["kv_raw"][i], block_n=128)
+            xn = ws["xn16"] if f16 else ws["xn"][i]
+            lib.layernorm_fwd(xa, pv[p + "0.norm.gamma"], xn, ws["xraw"][i], ws["st_a"][i], ycopy=ws["xn"][i] if dup else None)
+            lib.gemm(xn, pk["wq"], ws["q_raw"][i], block_n=self._bn_for(M, HD, d))
+            lib.gemm(ws["xraw"][i], pk["wkv_b"], ws["kv_raw"][i], block_n=128)
             lib.qk_l2norm_fwd(ws["q_raw"][i], ws["kv_raw"][i], pv[p + "0.q_scale"], pv[p + "0.k_scale"], ws["qn"][i], ws["kvn"][i], h)
             lib.attn_fwd_tc(ws["qn"][i], ws["kvn"][i], ws["table"], key_mask, ws["o"][i], ws["lse"][i], B, N, h)
-            lib.gemm(ws["o"][i], pk["wo"], xm, addend=xa, block_n=self._bn_for(M, d, HD))
-            lib.layernorm_fwd(xm, pv[p + "2.0.gamma"], ws["xn2"][i], None, ws["st_f"][i])
-            lib.gemm_ffn_up(ws["xn2"][i], pk["w1"], pk["conv"], ws["u"][i], ws["h"], ws["rowsum"], N, Fp)   # conv + GEGLU in the epilogue
-            lib.ffn_norm_fwd(ws["h"], ws["rowsum"], pk["gin"], ws["hn"][i], ws["st_i"][i], F, Fp, drop_p, self.seed, l,
-                             keep_bits=ws["keep"][i] if drop_p > 0 else None)
-            lib.gemm(ws["hn"][i], pk["w2"], xo, addend=xm, block_n=self._bn_for(M, d, Fp))
+            lib.gemm(ws["o"][i], pk["wo_b"], xm, addend=xa, block_n=self._bn_for(M, d, HD))
+            xn2 = ws["xn2_16"] if f16 else ws["xn2"][i]
+            lib.layernorm_fwd(xm, pv[p + "2.0.gamma"], xn2, None, ws["st_f"][i], ycopy=ws["xn2"][i] if dup else None)
+            lib.gemm_ffn_up(xn2, pk["w1"], pk["conv"], ws["u"][i], ws["h"], ws["rowsum"], N, Fp)   # conv + GEGLU in the epilogue
+            hn = ws["hn16"] if f16 else ws["hn"][i]
+            lib.ffn_norm_fwd(ws["h"], ws["rowsum"], pk["gin"], hn, ws["st_i"][i], F, Fp, drop_p, self.seed, l,
+                             keep_bits=ws["keep"][i] if drop_p > 0 else None, hn_copy=ws["hn"][i] if dup else None)
+            lib.gemm(hn, pk["w2"], xo, addend=xm, block_n=self._bn_for(M, d, Fp))
         x_last = x[2 * self.L] if train else x[0]
-        lib.layernorm_fwd(x_last, pv["transformer.norm.gamma"], ws["xf"], None, ws["st_o"], pl.dest_row)
+        xf = ws["xf16"] if f16 else ws["xf"]
+        lib.layernorm_fwd(x_last, pv["transformer.norm.gamma"], xf, None, ws["st_o"], pl.dest_row, ycopy=ws["xf"] if dup else None)
         for gi, (s, qi, cnt, base) in enumerate(pl.groups):
             if groups_wanted is not None and s not in groups_wanted:
                 continue
             rows = B * cnt
-            lib.gemm(ws["xf"][base:base + rows], self.pk_logit[s][qi], ws["logits"][gi], block_n=128)
+            lib.gemm(xf[base:base + rows], self.pk_logit[s][qi], ws["logits"][gi], block_n=128)
 
     # ------------------------------------------------------------------------------------------ backward
     def _wgrad(self, dy, x, gout, m, n, **kw):
@@ -333,7 +374,7 @@ class Engine:
                 continue
             rows = B * cnt
             dl = ws["dlogits"][gi]
-            lib.gemm(dl, self.pk_logit[s][qi], ws["dxf"][base:base + rows], b_mn=True, M=rows, N=d, K=self.Cp[s], block_n=128)
+            lib.gemm(dl, self.pk_logit_b[s][qi], ws["dxf"][base:base + rows], b_mn=True, M=rows, N=d, K=self.Cp[s], block_n=128)
             self._wgrad(dl, ws["xf"][base:base + rows], gv[f"logit_weights.{s}"][qi], self.Cp[s], d, row_split=self.Cp[s], row_valid=self.C[s])
         dxa, dxb = ws["dx"]
         lib.layernorm_bwd(ws["dxf"], x[2 * self.L], ws["st_o"], pv["transformer.norm.gamma"], dxa, gv["transformer.norm.gamma"],
@@ -343,26 +384,26 @@ class Engine:
             p, pk = f"transformer.layers.{l}.", self.pk[l]
             xa, xm = x[2 * l], x[2 * l + 1]
             # ---- conv feed-forward
-            lib.gemm(ws["dx_bf"], pk["w2"], ws["dhn"], b_mn=True, M=M, N=Fp, K=d, block_n=self._bn_for(M, Fp, d))
+            lib.gemm(ws["dx_bf"], pk["w2_b"], ws["dhn"], b_mn=True, M=M, N=Fp, K=d, block_n=self._bn_for(M, Fp, d))
             self._wgrad(ws["dx_bf"], ws["hn"][l], gv[p + "2.6.weight"], d, Fp, n_valid=F)
             ws["dgin"].zero_(); ws["dconv"].zero_()
             lib.ffn_mid_bwd(ws["dhn"], ws["hn"][l], ws["u"][l], ws["st_i"][l], pk["conv"], pk["gin"], ws["rowstat"], ws["du"],
                             ws["dgin"], ws["dconv"], B, N, F, Fp, drop_p, keep_bits=ws["keep"][l] if drop_p > 0 else None)
             lib.unpack_add(ws["dgin"], 1, Fp, gv[p + "2.4.gamma"], F, 1, F)
             lib.unpack_add(ws["dconv"], 2 * Fp, 3, gv[p + "2.2.ds_conv.weight"], 3, 2 * F, 3, split_dst=-1, split_src=F)
-            lib.gemm(ws["du"], pk["w1"], ws["dxn"], b_mn=True, M=M, N=d, K=2 * Fp, block_n=self._bn_for(M, d, 2 * Fp))
+            lib.gemm(ws["du"], pk["w1_b"], ws["dxn"], b_mn=True, M=M, N=d, K=2 * Fp, block_n=self._bn_for(M, d, 2 * Fp))
             self._wgrad(ws["du"], ws["xn2"][l], gv[p + "2.1.weight"], 2 * Fp, d, row_split=-1, row_valid=F)
             lib.layernorm_bwd(ws["dxn"], xm, ws["st_f"][l], pv[p + "2.0.gamma"], dxb, gv[p + "2.0.gamma"], dres=dxa, dx_bf16=ws["dx_bf"])
             # ---- attention
-            lib.gemm(ws["dx_bf"], pk["wo"], ws["d_o"], b_mn=True, M=M, N=HD, K=d, block_n=self._bn_for(M, HD, d))
+            lib.gemm(ws["dx_bf"], pk["wo_b"], ws["d_o"], b_mn=True, M=M, N=HD, K=d, block_n=self._bn_for(M, HD, d))
             self._wgrad(ws["dx_bf"], ws["o"][l], gv[p + "0.to_out.0.weight"], d, HD)
             ws["dqn"].zero_(); ws["dkvn"].zero_()
             lib.attn_bwd_tc(ws["qn"][l], ws["kvn"][l], ws["d_o"], ws["o"][l], ws["lse"][l], ws["table"], key_mask, ws["dsum"],
-                            ws["ds"], ws["dqn"], ws["dkvn"], ws["dtable"], B, N, h)
+                            ws["dqn"], ws["dkvn"], ws["dtable"], B, N, h)
             lib.qk_l2norm_bwd(ws["dqn"], ws["dkvn"], ws["q_raw"][l], ws["kv_raw"][l], pv[p + "0.q_scale"], pv[p + "0.k_scale"],
                               ws["dq_raw"], ws["dkv_raw"], gv[p + "0.q_scale"], gv[p + "0.k_scale"], h)
-            lib.gemm(ws["dq_raw"], pk["wq"], ws["dxn"], b_mn=True, M=M, N=d, K=HD, block_n=self._bn_for(M, d, HD))
-            lib.gemm(ws["dkv_raw"], pk["wkv"], ws["dxraw"], b_mn=True, M=M, N=d, K=128, block_n=self._bn_for(M, d, 128))
+            lib.gemm(ws["dq_raw"], pk["wq_b"], ws["dxn"], b_mn=True, M=M, N=d, K=HD, block_n=self._bn_for(M, d, HD))
+            lib.gemm(ws["dkv_raw"], pk["wkv_b"], ws["dxraw"], b_mn=True, M=M, N=d, K=128, block_n=self._bn_for(M, d, 128))
             self._wgrad(ws["dq_raw"], ws["xn"][l], gv[p + "0.to_q.weight"], HD, d)
             self._wgrad(ws["dkv_raw"], ws["xraw"][l], gv[p + "0.to_kv.weight"], 128, d)
             lib.layernorm_bwd(ws["dxn"], xa, ws["st_a"][l], pv[p + "0.norm.gamma"], dxa, gv[p + "0.norm.gamma"], dres=dxb, draw=ws["dxraw"],
@@ -381,13 +422,21 @@ class Engine:
         d_cur, d_nxt = ws["rp_d0"], ws["rp_d1"]
         lib.sgemm_small(dT, (1, N), pv[pre + "3.weight"], (Hr, 1), d_cur, (Hr, 1), N, Hr, h)                      # da3 = dY W4
         for j in (2, 1, 0):
-            lib.silu_bwd(d_cur, ws["rp_z"][j], d_cur, ws["rp_dz_bf"] if j > 0 else None)                           # dz_j
+            lib.silu_bwd(d_cur, ws["rp_z"][j], d_cur)                                                              # dz_j (fp32, in place)
             lib.colsum(d_cur, Hr, 1, gv[f"{pre}{j}.0.bias"], N, Hr, accumulate=True)
             if j > 0:
-                a_hi = ws["rp_a3"][j - 1][:, :Hr]          # bf16 hi part of a_{j-1}, saved by the forward split
+                # bf16x3 products, as in the forward pass (x y ~ x_hi y_hi + x_hi y_lo + x_lo y_hi: fp32-class): these
+                # gradients are sums of cancelling terms, so a plain bf16 operand rounding shows up amplified
+                lib.split3_bf16(d_cur, ws["rp_dz3"])                                                               # [hi | hi | lo]
+                dz_hi, dz_lo = ws["rp_dz3"][:, :Hr], ws["rp_dz3"][:, 2 * Hr:]
+                a_hi, a_lo = ws["rp_a3"][j - 1][:, :Hr], ws["rp_a3"][j - 1][:, 2 * Hr:]                            # forward split of a_{j-1}
+                w_hi, w_lo = self.pk_rp[j - 1][:, :Hr], self.pk_rp[j - 1][:, Hr:2 * Hr]                            # [hi | lo | hi]
                 gw = gv[f"{pre}{j}.0.weight"]
-                lib.gemm(ws["rp_dz_bf"], a_hi, gw, a_mn=True, b_mn=True, M=Hr, N=Hr, K=N, addend=gw, block_n=128)  # dW_j += dz^T a
-                lib.gemm(ws["rp_dz_bf"], self.pk_rp[j - 1][:, :Hr], d_nxt, b_mn=True, M=N, N=Hr, K=Hr, block_n=128)  # da = dz W_hi
+                for dz, a in ((dz_hi, a_hi), (dz_hi, a_lo), (dz_lo, a_hi)):                                         # dW_j += dz^T a
+                    lib.gemm(dz, a, gw, a_mn=True, b_mn=True, M=Hr, N=Hr, K=N, addend=gw, block_n=128)
+                lib.gemm(dz_hi, w_hi, d_nxt, b_mn=True, M=N, N=Hr, K=Hr, block_n=128)                               # da = dz W
+                lib.gemm(dz_hi, w_lo, d_nxt, b_mn=True, M=N, N=Hr, K=Hr, addend=d_nxt, block_n=128)
+                lib.gemm(dz_lo, w_hi, d_nxt, b_mn=True, M=N, N=Hr, K=Hr, addend=d_nxt, block_n=128)
                 d_cur, d_nxt = d_nxt, d_cur
             else:
                 lib.sgemm_small(d_cur, (1, Hr), ws["rp_in"], (1, 1), gv[f"{pre}0.0.weight"], (1, 1), Hr, 1, N, accumulate=True)
@@ -402,7 +451,8 @@ class Engine:
             mask_in = self_attn_mask.to(self.dev).to(torch.uint8).contiguous()
         _, src_row, key_mask, _, n_tok = lib.token_plan(
             ids, [s.codebook_size for s in self.seqs], [s.num_quantizers for s in self.seqs], self.emb_row_base,
-            self.start_row, append_eos=False, drop_last=False, mask_cond=False, mask_in=mask_in, want_labels=False)
+            self.start_row, append_eos=False, drop_last=False, mask_cond=False, mask_in=mask_in, want_labels=False,
+            err_flag=self.err_flag)
         pl = self.plan(B, n_tok)
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self._param_list)
         wanted = {len(self.seqs) - 1} if only_final else set(range(len(self.seqs)))

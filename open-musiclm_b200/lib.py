@@ -68,14 +68,19 @@ def call(name, *args):
     _check(rc, name)
 
 
+_T16 = (torch.bfloat16, torch.float16)
+FMT = {torch.bfloat16: 0, torch.float32: 1, torch.float16: 2}      # kFmtBF16 / kFmtF32 / kFmtF16 (csrc/common.cuh)
+
+
 def device_check():
     call("omlm_device_check")
 
 
 def gemm(a, b, out, *, a_mn=False, b_mn=False, M=None, N=None, K=None, addend=None, alpha=1.0,
          splits=1, row_split=0, row_valid=0, n_valid=0, block_n=128, max_ctas=0):
-    """out[m,n] = alpha * sum_k A(m,k) B(n,k) (+ addend).  a: [M,K] (or [K,M] if a_mn); b: [N,K] (or [K,N] if b_mn)."""
-    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    """out[m,n] = alpha * sum_k A(m,k) B(n,k) (+ addend).  a: [M,K] (or [K,M] if a_mn); b: [N,K] (or [K,N] if b_mn).
+    Each operand is bf16 or fp16 (its torch dtype decides the tensor-core operand format), fp32 accumulation."""
+    assert a.dtype in _T16 and b.dtype in _T16
     assert a.stride(-1) == 1 and b.stride(-1) == 1 and out.stride(-1) == 1
     if M is None:
         M = a.shape[1] if a_mn else a.shape[0]
@@ -85,7 +90,8 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, M=None, N=None, K=None, addend=No
         N = b.shape[1] if b_mn else b.shape[0]
     out_f32 = 1 if out.dtype == torch.float32 else 0
     assert out_f32 or out.dtype == torch.bfloat16
-    call("omlm_gemm_bf16", _p(a), _I(int(a_mn)), _L(a.stride(0)), _p(b), _I(int(b_mn)), _L(b.stride(0)),
+    call("omlm_gemm16", _p(a), _I(int(a.dtype == torch.float16)), _I(int(a_mn)), _L(a.stride(0)),
+         _p(b), _I(int(b.dtype == torch.float16)), _I(int(b_mn)), _L(b.stride(0)),
          _I(M), _I(N), _I(K), _p(out), _I(out_f32), _L(out.stride(0)),
          _p(addend), _L(addend.stride(0) if addend is not None else 0), _F(alpha), _I(splits),
          _I(row_split), _I(row_valid), _I(n_valid), _I(block_n), _I(max_ctas), _stream())
@@ -99,7 +105,7 @@ _ULL = ctypes.c_ulonglong
 
 
 def token_plan(ids_list, codebooks, nqs, emb_row_base, start_row, *, append_eos, drop_last, mask_cond,
-               pad_id=-1, mask_in=None, forget_keep=None, want_labels=True):
+               pad_id=-1, mask_in=None, forget_keep=None, want_labels=True, err_flag=None):
     """Returns ids_out [B, sum n_tok] int64, src_row [B,N] int32, key_mask [B,N] uint8, labels [B, sum(len+eos)] int32."""
     S = len(ids_list)
     B = ids_list[0].shape[0]
@@ -118,7 +124,7 @@ def token_plan(ids_list, codebooks, nqs, emb_row_base, start_row, *, append_eos,
     arr = lambda v: (ctypes.c_int * S)(*[int(x) for x in v])
     call("omlm_token_plan", _I(S), ptrs, arr(lens), arr(codebooks), arr(nqs), arr(emb_row_base), arr(start_row),
          _I(B), _I(int(append_eos)), _I(int(drop_last)), _I(int(mask_cond)), _I(pad_id), _p(mask_in), _p(forget_keep),
-         _p(ids_out), _p(src_row), _p(key_mask), _p(labels), _stream())
+         _p(ids_out), _p(src_row), _p(key_mask), _p(labels), _p(err_flag), _stream())
     return ids_out, src_row, key_mask, labels, n_tok
 
 
@@ -138,9 +144,12 @@ def embed_scatter_add(dtable, src_row, dx, scale):
     call("omlm_embed_scatter_add", _p(dtable), _p(src_row), _p(dx), _I(M), _I(D), _F(scale), _stream())
 
 
-def layernorm_fwd(x, gamma, y, xraw=None, stats=None, dest_row=None):
+def layernorm_fwd(x, gamma, y, xraw=None, stats=None, dest_row=None, ycopy=None):
+    """y: fp16 or bf16 (its dtype decides); ycopy: optional bf16 duplicate of y for the backward GEMMs."""
     M, D = x.shape
-    call("omlm_layernorm_fwd", _p(x), _p(gamma), _p(y), _p(xraw), _p(stats), _p(dest_row), _I(M), _I(D), _stream())
+    assert y.dtype in _T16 and (xraw is None or xraw.dtype == torch.bfloat16) and (ycopy is None or ycopy.dtype == torch.bfloat16)
+    call("omlm_layernorm_fwd", _p(x), _p(gamma), _p(y), _I(int(y.dtype == torch.float16)), _p(ycopy), _p(xraw), _p(stats),
+         _p(dest_row), _I(M), _I(D), _stream())
 
 
 def layernorm_bwd(dy, x, stats, gamma, dx, dgamma, dres=None, draw=None, src_row=None, dx_bf16=None):
@@ -201,25 +210,28 @@ def attn_bwd(qn, kvn, d_o, o, lse2, table, key_mask, dsum_scratch, dqn, dkvn, dt
          _p(dsum_scratch), _p(dqn), _p(dkvn), _p(dtable), _I(B), _I(N), _I(heads), _F(scale), _stream())
 
 
-def attn_bwd_tc(qn, kvn, d_o, o, lse2, table, key_mask, dsum_scratch, ds_scratch, dqn, dkvn, dtable, B, N, heads, scale=8.0):
+def attn_bwd_tc(qn, kvn, d_o, o, lse2, table, key_mask, dsum_scratch, dqn, dkvn, dtable, B, N, heads, scale=8.0):
     call("omlm_attn_bwd_tc", _p(qn), _p(kvn), _p(d_o), _p(o), _p(lse2), _p(table), _I(table.stride(0)), _p(key_mask),
-         _p(dsum_scratch), _p(ds_scratch), _p(dqn), _p(dkvn), _p(dtable), _I(B), _I(N), _I(heads), _F(scale), _stream())
+         _p(dsum_scratch), _p(dqn), _p(dkvn), _p(dtable), _I(B), _I(N), _I(heads), _F(scale), _stream())
 
 
 def gemm_ffn_up(xn, w1_packed, conv_w_packed, u_out, h_out, rowsum, Nseq, Fp, max_ctas=0):
     M, K = xn.shape
+    assert xn.dtype in _T16 and xn.dtype == w1_packed.dtype == u_out.dtype == h_out.dtype
     call("omlm_gemm_ffn_up", _p(xn), _p(w1_packed), _p(conv_w_packed), _p(u_out), _p(h_out), _p(rowsum), _I(M), _I(Nseq),
-         _I(K), _I(Fp), _I(max_ctas), _stream())
+         _I(K), _I(Fp), _I(int(xn.dtype == torch.float16)), _I(max_ctas), _stream())
 
 
-def ffn_norm_fwd(h, rowsum, gamma, hn, stats, F, Fp, drop_p=0.0, seed=None, layer=0, keep_bits=None):
-    call("omlm_ffn_norm_fwd", _p(h), _p(rowsum), _p(gamma), _p(hn), _p(stats), _p(keep_bits), _L(h.shape[0]), _I(F), _I(Fp),
-         _F(drop_p), _p(seed), _I(layer), _stream())
+def ffn_norm_fwd(h, rowsum, gamma, hn, stats, F, Fp, drop_p=0.0, seed=None, layer=0, keep_bits=None, hn_copy=None):
+    assert h.dtype in _T16 and h.dtype == hn.dtype and (hn_copy is None or hn_copy.dtype == torch.bfloat16)
+    call("omlm_ffn_norm_fwd", _p(h), _p(rowsum), _p(gamma), _p(hn), _p(hn_copy), _p(stats), _p(keep_bits), _L(h.shape[0]),
+         _I(F), _I(Fp), _F(drop_p), _p(seed), _I(layer), _I(int(h.dtype == torch.float16)), _stream())
 
 
 def ffn_mid_bwd(dhn, hn, u, stats, conv_w, gamma, rowstat, du, dgamma, dconv_w, B, N, F, Fp, drop_p=0.0, keep_bits=None):
+    assert u.dtype in _T16 and hn.dtype == dhn.dtype == du.dtype == torch.bfloat16
     call("omlm_ffn_mid_bwd", _p(dhn), _p(hn), _p(u), _p(stats), _p(conv_w), _p(gamma), _p(keep_bits), _p(rowstat), _p(du),
-         _p(dgamma), _p(dconv_w), _I(B), _I(N), _I(F), _I(Fp), _F(drop_p), _stream())
+         _p(dgamma), _p(dconv_w), _I(B), _I(N), _I(F), _I(Fp), _F(drop_p), _I(int(u.dtype == torch.float16)), _stream())
 
 
 def cross_entropy(logits, labels, C, loss_acc, *, grad_scale=0.0, dlogits=None, ignore_index=-100, label_stride=1, rows=None):
@@ -238,7 +250,7 @@ def adamw_step(p, g, m, v, n_decay, hyper, sumsq):
 
 
 def pack(src, src_ld, rows_valid, cols_valid, dst, rows_p, cols_p, split_dst=0, split_src=0):
-    call("omlm_pack", _p(src), _L(src_ld), _I(rows_valid), _I(cols_valid), _p(dst), _I(int(dst.dtype == torch.float32)),
+    call("omlm_pack", _p(src), _L(src_ld), _I(rows_valid), _I(cols_valid), _p(dst), _I(FMT[dst.dtype]),
          _L(cols_p if dst.dim() == 1 else dst.stride(0)), _I(rows_p), _I(cols_p), _I(split_dst), _I(split_src), _stream())
 
 
@@ -246,30 +258,41 @@ class _PackJob(ctypes.Structure):
     _fields_ = [("src", ctypes.c_void_p), ("dst", ctypes.c_void_p), ("src_ld", ctypes.c_long), ("dst_ld", ctypes.c_long),
                 ("unit_start", ctypes.c_long), ("rows_valid", ctypes.c_int), ("cols_valid", ctypes.c_int),
                 ("rows_p", ctypes.c_int), ("cols_p", ctypes.c_int), ("split_dst", ctypes.c_int), ("split_src", ctypes.c_int),
-                ("dst_f32", ctypes.c_int), ("reserved", ctypes.c_int)]
+                ("dst_fmt", ctypes.c_int), ("reserved", ctypes.c_int)]
 
 
 class PackTable:
-    """Device-resident table of pack jobs (same arguments as pack()); run() repacks all of them in one launch."""
+    """Device-resident table of pack jobs (same arguments as pack()); run() repacks all of them in one launch per
+    MAX_JOBS jobs (a 24-layer model has ~170 jobs: one launch)."""
+    MAX_JOBS = 512      # kPackMaxJobs in csrc/optim.cu
 
     def __init__(self, device):
-        self.device, self.jobs, self.keep, self.units, self.table = device, [], [], 0, None
+        self.device, self.chunks, self.keep, self.tables = device, [[[], 0]], [], None
 
     def add(self, src, src_ld, rows_valid, cols_valid, dst, rows_p, cols_p, split_dst=0, split_src=0):
+        if len(self.chunks[-1][0]) == self.MAX_JOBS:
+            self.chunks.append([[], 0])
+        chunk = self.chunks[-1]
         dst_ld = cols_p if dst.dim() == 1 else dst.stride(0)
-        self.jobs.append(_PackJob(src.data_ptr(), dst.data_ptr(), src_ld, dst_ld, self.units, rows_valid, cols_valid, rows_p,
-                                  cols_p, split_dst, split_src, int(dst.dtype == torch.float32), 0))
+        chunk[0].append(_PackJob(src.data_ptr(), dst.data_ptr(), src_ld, dst_ld, chunk[1], rows_valid, cols_valid, rows_p,
+                                 cols_p, split_dst, split_src, FMT[dst.dtype], 0))
         self.keep.append((src, dst))
-        self.units += (rows_p * ((cols_p + 3) // 4) + 255) // 256
-        self.table = None
+        chunk[1] += (rows_p * ((cols_p + 3) // 4) + 255) // 256
+        self.tables = None
+
+    @property
+    def n_jobs(self):
+        return sum(len(c[0]) for c in self.chunks)
 
     def run(self):
-        if self.table is None:
-            arr = (_PackJob * len(self.jobs))(*self.jobs)
-            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
-            self.table = host.to(self.device)
-        assert 0 < len(self.jobs) <= 64, "omlm_pack_multi takes at most 64 jobs per table"
-        call("omlm_pack_multi", ctypes.c_void_p(self.table.data_ptr()), _I(len(self.jobs)), _L(self.units), _stream())
+        if self.tables is None:
+            self.tables = []
+            for jobs, units in self.chunks:
+                arr = (_PackJob * len(jobs))(*jobs)
+                host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+                self.tables.append((host.to(self.device), len(jobs), units))
+        for table, n, units in self.tables:
+            call("omlm_pack_multi", ctypes.c_void_p(table.data_ptr()), _I(n), _L(units), _stream())
 
 
 def unpack_add(packed, rows_p, cols_p, dst, dst_ld, rows_valid, cols_valid, split_dst=0, split_src=0):

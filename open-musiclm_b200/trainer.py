@@ -53,6 +53,12 @@ class HotPathTrainer:
         self.pg = process_group
         self.world, self.rank = world_info(process_group)
         eng.seed.fill_(rank_seed(seed, self.rank))     # per-rank random streams (dropout / forgetful mask)
+        if self.world > 1:
+            # replicas must start from the same weights (DDP broadcasts rank 0's at wrap time, trainer.py:154-155 via
+            # accelerate.prepare): do not rely on every rank having seeded its initialisation identically
+            dist.broadcast(eng.arena_p, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0,
+                           group=process_group)
+            eng.refresh_packed(force=True)
         eng.adam_m = torch.zeros_like(eng.arena_p)
         eng.adam_v = torch.zeros_like(eng.arena_p)
         # PAGEABLE on purpose: cudaMemcpyAsync stages a pageable source before it returns, so the host may already write
@@ -77,6 +83,8 @@ class HotPathTrainer:
         # shapes are static per configuration: N is known before the plan kernel runs
         n_tok = [t.shape[1] + 1 - (1 if s == S - 1 else 0) for s, t in enumerate(ids)]
         pl = eng.plan(B, n_tok)
+        if train:
+            eng.seed += 1       # device-side: every micro-batch draws its own dropout / forgetful masks (also under graph replay)
         forget = None
         if train and self.mask_prob > 0:
             num_drop = min(int(pl.N * self.mask_prob), pl.N - 1)        # utils.py:53
@@ -84,7 +92,8 @@ class HotPathTrainer:
             forget = lib.forgetful_mask(B, pl.N, num_drop, eng.seed, self._mask_draws, dev)
         _, src_row, key_mask, labels, _ = lib.token_plan(
             ids, [s.codebook_size for s in eng.seqs], [s.num_quantizers for s in eng.seqs], eng.emb_row_base,
-            eng.start_row, append_eos=True, drop_last=True, mask_cond=True, pad_id=self.pad_id, forget_keep=forget)
+            eng.start_row, append_eos=True, drop_last=True, mask_cond=True, pad_id=self.pad_id, forget_keep=forget,
+            err_flag=eng.err_flag)
         ws = eng.workspace(pl, backward)
         weighted = {s for s in range(S) if self.ce_weights[s] > 0}
         drop = train and eng.drop_p > 0
@@ -129,8 +138,6 @@ class HotPathTrainer:
 
     def _fwd_bwd_body(self, micro_batches):
         """Device work of one optimiser step up to the gradient arena (capturable in a CUDA graph)."""
-        eng = self.eng
-        eng.seed += 1
         for i, mb in enumerate(micro_batches):
             self._micro_batch(mb, True, i, True)
 
@@ -159,7 +166,8 @@ class HotPathTrainer:
         assert len(micro_batches) == self.grad_accum_every
         eng = self.eng
         self.transformer.train()
-        self._set_hyper()
+        eng.refresh_packed()        # no-op unless the parameters were written from outside (load_state_dict, manual edits):
+        self._set_hyper()           # the captured graphs re-pack only after their own optimiser update
         if not self.use_cuda_graph:
             self._step_body(micro_batches)
             self.steps += 1
@@ -223,3 +231,35 @@ class HotPathTrainer:
 
     def grad_norm(self):
         return torch.sqrt(self.eng.sumsq).float()
+
+    # ------------------------------------------------------------------------------------------- checkpointing
+    def state_dict(self):
+        """Optimiser / scheduler / RNG state needed to resume training exactly where it stopped (the reference's
+        SingleStageTrainer.save keeps optim + scheduler state next to the model, trainer.py:359-391).
+        Layout: torch.optim.AdamW-style — per-parameter 'exp_avg' / 'exp_avg_sq' keyed by the parameter's state_dict
+        name plus the shared step count (the reference steps all parameters together), so it converts to a torch
+        optimizer state by a dict comprehension."""
+        eng = self.eng
+        state = {}
+        for n, p in self.transformer.named_parameters():
+            o = eng.layout[n]
+            state[n] = {"step": self.steps, "exp_avg": eng.adam_m[o:o + p.numel()].view(p.shape).clone(),
+                        "exp_avg_sq": eng.adam_v[o:o + p.numel()].view(p.shape).clone()}
+        return {"state": state, "steps": self.steps, "seed": int(eng.seed.item()), "mask_draws": self._mask_draws,
+                "hparams": dict(lr=self.lr, lr_warmup=self.lr_warmup, wd=self.wd, betas=tuple(self.betas), eps=self.eps,
+                                max_grad_norm=self.max_grad_norm, grad_accum_every=self.grad_accum_every)}
+
+    def load_state_dict(self, sd):
+        """Inverse of state_dict().  Also call after transformer.load_state_dict(): the packed 16-bit weights are
+        refreshed here, so graphs captured earlier stay valid."""
+        eng = self.eng
+        for n, p in self.transformer.named_parameters():
+            o = eng.layout[n]
+            st = sd["state"][n]
+            eng.adam_m[o:o + p.numel()].view(p.shape).copy_(st["exp_avg"])
+            eng.adam_v[o:o + p.numel()].view(p.shape).copy_(st["exp_avg_sq"])
+        self.steps = int(sd["steps"])
+        eng.seed.fill_(int(sd["seed"]))
+        self._mask_draws = int(sd["mask_draws"])
+        eng.arena_g.zero_()
+        eng.refresh_packed(force=True)

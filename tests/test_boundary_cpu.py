@@ -24,7 +24,7 @@ def test_abi_library_exports_every_declared_symbol():
     assert len(syms) >= 25
     for s in syms:
         assert hasattr(l, s), f"{s} declared in include/omlm_b200.h but not exported"
-    assert l.omlm_abi_version() == 1
+    assert l.omlm_abi_version() == 2
     l.omlm_last_error.restype = ctypes.c_char_p
     assert isinstance(l.omlm_last_error(), bytes)
 

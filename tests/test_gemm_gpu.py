@@ -29,6 +29,29 @@ def test_gemm_majors(a_mn, b_mn, block_n, M, N, K):
         assert err < (6e-3 if dtype == torch.bfloat16 else 1e-5), (a_mn, b_mn, block_n, M, N, K, dtype, err)
 
 
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
+def test_gemm_fp16_operands(a_mn, b_mn):
+    """tcgen05 kind::f16 with fp16 operands (instruction-descriptor format bits) — the forward GEMMs of the hot path.
+    Mixed fp16 x bf16 is rejected on the host: B200 raises an illegal-instruction fault for it (measured in round 2)."""
+    from open_musiclm_b200 import lib
+    torch.manual_seed(11)
+    M, N, K = 384, 640, 520
+    # values that tell the formats apart: fp16 keeps 11 significant bits, bf16 8
+    A = (torch.randn(M, K, device="cuda") * 1.37).half()
+    B = (torch.randn(N, K, device="cuda") * 0.71).half()
+    ref = A.float() @ B.float().t()
+    a = A.t().contiguous() if a_mn else A
+    b = B.t().contiguous() if b_mn else B
+    for bn in (128, 256):
+        out = torch.full((M, N), float("nan"), device="cuda")
+        lib.gemm(a, b, out, a_mn=a_mn, b_mn=b_mn, block_n=bn)
+        torch.cuda.synchronize()
+        err = _rel(out, ref)
+        assert err < 1e-5, (a_mn, b_mn, bn, err)      # exact products of the stored fp16 values, fp32 accumulate
+    with pytest.raises(lib.OmlmError):
+        lib.gemm(a.bfloat16(), b, out, a_mn=a_mn, b_mn=b_mn)
+
+
 def test_gemm_residual_and_splitk():
     from open_musiclm_b200 import lib
     torch.manual_seed(1)

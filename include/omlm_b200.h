@@ -24,6 +24,8 @@ const char* omlm_last_error(void);
 int omlm_abi_version(void);
 /* 0 iff the current CUDA device is compute capability 10.x. */
 int omlm_device_check(void);
+/* Number of SMs of the current device (the persistent kernels' default grid). */
+int omlm_num_sms(void);
 
 /* bf16 GEMM on tcgen05 tensor cores:  out[m,n] = alpha * sum_k A(m,k) * B(n,k) (+ addend[m,n]).
  *   a_mn_major = 0: A is [M, lda] with k contiguous;  1: A is [K, lda] with m contiguous.
@@ -70,9 +72,10 @@ int omlm_token_plan(int n_seqs, const long long* const* ids, const int* len, con
  * positions per row, never position 0.  seed: device pointer; stream_id separates draws. */
 int omlm_forgetful_mask(unsigned char* keep, int B, int N, int num_drop,
                         const unsigned long long* seed, unsigned long long stream_id, void* stream);
-/* x[m,:] = table[src_row[m],:] (fp32, 128-bit copies); replaces get_embeds + start-token concat
+/* x[m,:] = table[src_row[m],:] (+ table[src_row2[m],:] when src_row2 is given: the absolute position embeddings of
+ * open_musiclm.py:134-136; negative rows add nothing) (fp32, 128-bit copies); replaces get_embeds + start-token concat
  * (open_musiclm.py:133-145).  scatter_add is its backward incl. the grad_shrink factor (utils.py:60-61). */
-int omlm_embed_gather(const float* table, const int* src_row, float* x, int M, int D, void* stream);
+int omlm_embed_gather(const float* table, const int* src_row, const int* src_row2, float* x, int M, int D, void* stream);
 int omlm_embed_scatter_add(float* dtable, const int* src_row, const float* dx, int M, int D,
                            float scale, void* stream);
 
@@ -182,6 +185,37 @@ int omlm_pack(const float* src, long src_ld, int rows_valid, int cols_valid, voi
               int rows_p, int cols_p, int split_dst, int split_src, void* stream);
 int omlm_unpack_add(const float* packed, long p_ld, int rows_p, int cols_p, float* dst, long dst_ld, int rows_valid,
                     int cols_valid, int split_dst, int split_src, void* stream);
+
+/* ---- incremental (KV-cache) decoding: TokenConditionedTransformerWrapper.generate (open_musiclm.py:253-326) ----------
+ * One new position per sequence and step instead of the reference's full-prefix forward per sampled token
+ * (open_musiclm.py:303-307).  B <= 16 rows; SIMT weight-streaming kernels (csrc/decode.cu).
+ * out[b, n] = A[b, :] . W[n, :] (+ addend[b, n]);  W 16-bit [N, ldw] (w_f16: fp16, else bf16).  prologue builds the
+ * activation rows in W's format: 0 = A already 16-bit [B, lda];  1 = A fp32, rounded;  2 = LayerNorm(A fp32) * gamma
+ * (transformer.py:24-31);  3 = A = h 16-bit [B, K] with the fused per-128-channel sums rowsum [B, K/128, 2]:
+ * (h - mean) * rstd * gamma with n_real = F live channels (the inner LayerNorm of ConvFeedForward, transformer.py:147).
+ * out_fmt: 0 bf16, 1 fp32, 2 fp16. */
+int omlm_skinny_gemm(const void* A, long lda, int prologue, const void* W, long ldw, int w_f16, const float* gamma,
+                     const float* rowsum, int n_real, const float* addend, long ldadd, void* out, int out_fmt, long ldo,
+                     int B, int N, int K, void* stream);
+/* Attention for the new position n = *pos_ptr (device int): q_raw [B, heads*64], kv_raw [B, 128] bf16 are this step's
+ * un-normalised projections; they are l2-normalised * scale (transformer.py:269-271), [k | v] is appended to
+ * cache [B, cache_ld_b/128 positions, 128] bf16 at n, then softmax(8 q.k_j + table[head, n-j]) V over keys 0..n
+ * (transformer.py:304-331, no key mask: generate passes none).  max_pos bounds n + 1 (shared-memory scores). */
+int omlm_attn_decode(const void* q_raw, const void* kv_raw, const float* q_scale, const float* k_scale, void* cache,
+                     long cache_ld_b, const float* table, int table_ld, const int* pos_ptr, int max_pos, void* out, int B,
+                     int heads, float scale, void* stream);
+/* CausalDSConv + GEGLU for one new row (transformer.py:122-137): u_new [B, 2Fp] against state [B, 2, 2Fp] (rows t-2, t-1,
+ * shifted in place) -> h [B, Fp], rowsum [B, Fp/128, 2]. */
+int omlm_decode_conv_geglu(const void* u_new, void* state, const float* conv_w, void* h_out, float* rowsum, int B, int Fp,
+                           int act_f16, void* stream);
+/* Sampling of one token per sequence (open_musiclm.py:309-319, utils.py:71-84): eos (class C-1) forbidden unless
+ * allow_eos, top-k with the given k, Gumbel-argmax at `temperature`.  uniform: optional [steps, B, C] uniform(0,1) draws
+ * (slice *step_ptr is used; reproduces a given torch stream), else a Philox stream keyed by *seed.  Writes
+ * tokens[b, *step_ptr] and next_row[b] = row_offset + token (embedding-table row for the next step), then advances
+ * step_ptr[0] (step_ptr[1] is scratch) and, when given, pos_ptr[0]. */
+int omlm_sample(const float* logits, long ld, int C, int top_k, float temperature, int allow_eos, const float* uniform,
+                const unsigned long long* seed, long long* tokens, long tokens_ld, int* next_row, int row_offset, int* step_ptr,
+                int* pos_ptr, int B, void* stream);
 
 #ifdef __cplusplus
 }

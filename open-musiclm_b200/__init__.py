@@ -6,9 +6,11 @@ Only what the TokenConditionedTransformer training path needs lives here:
   engine.py   parameter arena, packed weights, kernel sequencing (forward / backward)
   model.py    drop-in `TokenConditionedTransformer`, `create_{semantic,coarse,fine}_transformer`
   trainer.py  B200-native SingleStageTrainer step loop (`HotPathTrainer`)
+  decode.py   `TokenConditionedTransformerWrapper.generate`: KV-cache autoregressive decoding
 """
 __version__ = "0.1.0"
 
 from .model import (TokenConditionedTransformer, TokenSequenceInfo, create_coarse_transformer,  # noqa: F401
                     create_fine_transformer, create_semantic_transformer)
 from .trainer import HotPathTrainer  # noqa: F401
+from .decode import TokenConditionedTransformerWrapper  # noqa: F401

@@ -86,6 +86,8 @@ const char* omlm_last_error(void) { return omlm::g_err; }
 
 int omlm_abi_version(void) { return OMLM_B200_ABI_VERSION; }
 
+int omlm_num_sms(void) { return omlm::num_sms(); }
+
 int omlm_device_check(void) {
   int dev = 0;
   OMLM_CUDA(cudaGetDevice(&dev));

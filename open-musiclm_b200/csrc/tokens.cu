@@ -105,9 +105,10 @@ __global__ void forgetful_mask_kernel(unsigned char* __restrict__ keep, int N, i
   }
 }
 
-// x[m, :] = table[src_row[m], :]  (zero row for src_row < 0).  fp32 table, fp32 out; 128-bit copies.
+// x[m, :] = table[src_row[m], :] (+ table[src_row2[m], :]: absolute position embeddings, open_musiclm.py:134-136);
+// a negative row contributes zero.  fp32 table, fp32 out; 128-bit copies.
 __global__ void embed_gather_kernel(const float* __restrict__ table, const int* __restrict__ src_row,
-                                    float* __restrict__ x, int M, int D) {
+                                    const int* __restrict__ src_row2, float* __restrict__ x, int M, int D) {
   const int vec_per_row = D >> 2;
   const long long total = static_cast<long long>(M) * vec_per_row;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -116,6 +117,13 @@ __global__ void embed_gather_kernel(const float* __restrict__ table, const int* 
     const int r = src_row[m];
     float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r >= 0) val = reinterpret_cast<const float4*>(table + static_cast<long long>(r) * D)[v];
+    if (src_row2 != nullptr) {
+      const int r2 = src_row2[m];
+      if (r2 >= 0) {
+        const float4 p = reinterpret_cast<const float4*>(table + static_cast<long long>(r2) * D)[v];
+        val.x += p.x; val.y += p.y; val.z += p.z; val.w += p.w;
+      }
+    }
     reinterpret_cast<float4*>(x + static_cast<long long>(m) * D)[v] = val;
   }
 }
@@ -181,12 +189,12 @@ int omlm_forgetful_mask(unsigned char* keep, int B, int N, int num_drop,
   return 0;
 }
 
-int omlm_embed_gather(const float* table, const int* src_row, float* x, int M, int D, void* stream) {
+int omlm_embed_gather(const float* table, const int* src_row, const int* src_row2, float* x, int M, int D, void* stream) {
   using namespace omlm;
   OMLM_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0, "embed_gather: bad shape %d x %d", M, D);
   const long long total = static_cast<long long>(M) * (D / 4);
   const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(num_sms()) * 16));
-  embed_gather_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(table, src_row, x, M, D);
+  embed_gather_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(table, src_row, src_row2, x, M, D);
   OMLM_LAUNCH_CHECK();
   return 0;
 }

@@ -1,11 +1,18 @@
 """Host-side pieces of the data-parallel path (device-agnostic so that they can be exercised under gloo on CPU).
 
-The hot path shards by batch: every rank runs the same step on its own sequences, gradients are summed over
-ranks with ONE all-reduce of the flat fp32 arena per optimiser step, and the DDP-mean 1/world factor is folded into
-the clip/AdamW kernel (trainer.py:154-155,439 of the reference -> HotPathTrainer.train_step).
+The hot path shards by batch: every rank runs the same step on its own sequences and the gradients are summed over
+ranks (DDP mean: the 1/world factor is folded into the clip/AdamW kernel; trainer.py:154-155,439 of the reference).
+The sum is an all-reduce of the flat fp32 gradient arena, cut into BUCKETS that follow the order in which the backward
+pass finishes them — logit heads, then the layers from last to first, then everything that completes at the very end
+(embeddings, start tokens, the rel-pos MLP, the small 1-D parameters) — so that each bucket's all-reduce runs on a
+side stream underneath the rest of the backward pass and only the last one is exposed.
 """
+from typing import Dict, List, Sequence, Tuple
+
 import torch
 import torch.distributed as dist
+
+Slice = Tuple[int, int]
 
 
 def world_info(group=None):
@@ -31,3 +38,93 @@ def grad_prescale(group=None) -> float:
 def rank_seed(seed: int, rank: int) -> int:
     """Per-rank seed of the dropout / forgetful-mask streams (weights use the SAME seed on every rank)."""
     return seed * 1000003 + rank * 7919 + 1
+
+
+def plan_buckets(layout: Dict[str, int], sizes: Dict[str, int], total: int, depth: int,
+                 min_elems: int = 4 << 20) -> List[Tuple[str, List[Slice]]]:
+    """Cuts the gradient arena [0, total) into all-reduce buckets in backward-completion order.
+
+    layout / sizes: arena offset and element count of every parameter (state_dict names).  Returns
+    [(trigger, [(start, end), ...]), ...] where trigger names the point of the backward pass after which the bucket is
+    complete: 'heads', 'layer<l>' (l = depth-1 .. 0) or 'tail'.  Every arena element (padding included: it is zero on
+    all ranks) belongs to exactly one bucket.  Layer buckets smaller than min_elems are merged into the next one, so a
+    shallow toy model reduces in one or two calls while a 24-layer model gets ~24 of ~40 MB each."""
+    def span(names: Sequence[str]) -> Slice:
+        lo = min(layout[n] for n in names)
+        hi = max(layout[n] + sizes[n] for n in names)
+        return lo, hi
+
+    mats = lambda l: [n for n in layout if n.startswith(f"transformer.layers.{l}.") and n.endswith("weight")]
+    heads = [n for n in layout if n.startswith("logit_weights.")]
+    claimed: List[Slice] = []
+    out: List[Tuple[str, List[Slice]]] = []
+    if heads:
+        out.append(("heads", [span(heads)]))
+        claimed.append(span(heads))
+    pending: List[Slice] = []
+    pend_elems = 0
+    for l in reversed(range(depth)):
+        s = span(mats(l))
+        pending.append(s)
+        pend_elems += s[1] - s[0]
+        if pend_elems >= min_elems or l == 0:
+            # adjacent layer spans are contiguous in the arena: merge them into one slice
+            lo, hi = min(p[0] for p in pending), max(p[1] for p in pending)
+            merged = [(lo, hi)] if hi - lo <= pend_elems + 64 * len(pending) else sorted(pending)
+            out.append((f"layer{l}", merged))
+            claimed.extend(merged)
+            pending, pend_elems = [], 0
+    # the tail: whatever is left, as maximal contiguous slices
+    claimed.sort()
+    tail, pos = [], 0
+    for lo, hi in claimed:
+        if lo > pos:
+            tail.append((pos, lo))
+        pos = max(pos, hi)
+    if pos < total:
+        tail.append((pos, total))
+    out.append(("tail", tail))
+    # sanity: exact cover of [0, total)
+    cover = sorted(s for _, sl in out for s in sl)
+    p = 0
+    for lo, hi in cover:
+        assert lo == p, f"bucket plan does not tile the arena at {p} (next slice starts at {lo})"
+        p = hi
+    assert p == total
+    return out
+
+
+class BucketReducer:
+    """Issues the per-bucket all-reduces.  `fire(trigger)` is called by the backward pass when the named point is
+    reached; on CUDA the collective is enqueued on `side_stream` after an event recorded on the compute stream, and
+    `join()` makes the compute stream wait for all of them (both work under CUDA-graph capture: fork / join).  On CPU
+    (gloo tests) everything is synchronous."""
+
+    def __init__(self, flat: torch.Tensor, plan, group=None, side_stream=None):
+        self.flat, self.plan, self.group, self.side = flat, {t: sl for t, sl in plan}, group, side_stream
+        self.order = [t for t, _ in plan]
+        self.world, _ = world_info(group)
+        self.fired: List[str] = []
+
+    def begin(self):
+        self.fired = []
+
+    def fire(self, trigger: str):
+        if trigger not in self.plan or self.world == 1:
+            return
+        self.fired.append(trigger)
+        views = [self.flat[lo:hi] for lo, hi in self.plan[trigger]]
+        if self.side is not None:
+            self.side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.side):
+                for v in views:
+                    dist.all_reduce(v, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            for v in views:
+                dist.all_reduce(v, op=dist.ReduceOp.SUM, group=self.group)
+
+    def join(self):
+        if self.world > 1:
+            assert self.fired == self.order, f"buckets fired {self.fired}, expected {self.order}"
+            if self.side is not None:
+                torch.cuda.current_stream().wait_stream(self.side)

@@ -68,6 +68,16 @@ class _Plan:
             self.seq_row_index.append(idx.to(device))
         self.rows_total = base
         self.dest_row = dest.reshape(-1).to(device)
+        # absolute position embeddings (open_musiclm.py:134-136): token t of sequence s also gets row t of its
+        # position table; start tokens get none.  Static per shape, so it is built here once.
+        self.src_row2 = None
+        if eng.abs_pos:
+            r2 = torch.full((B, self.N), -1, dtype=torch.int32)
+            for s in range(S):
+                if n_tok[s] > eng.max_abs_pos:
+                    raise IndexError(f"sequence {s} has {n_tok[s]} tokens but max_absolute_position_embeddings is {eng.max_abs_pos}")
+                r2[:, self.pos0[s] + 1:self.pos0[s] + 1 + n_tok[s]] = eng.abs_row_base[s] + torch.arange(n_tok[s], dtype=torch.int32)
+            self.src_row2 = r2.reshape(-1).to(device)
 
 
 def itertools_accumulate(xs):
@@ -92,7 +102,15 @@ class Engine:
         self.seqs = module.token_sequences
         self.d, self.L, self.h = module.dim, module.depth, module.heads
         self.HD = self.h * 64
-        self.F = int(self.d * 2 * 4 / 3)
+        self.use_conv_ff = bool(getattr(module, "use_conv_ff", True))
+        self.bias_type = getattr(module, "relative_position_bias_type", "continuous")
+        self.abs_pos = module.absolute_position_embeddings is not None
+        self.max_abs_pos = int(getattr(module, "max_absolute_position_embeddings", 0))
+        # feed-forward flavour (transformer.py:140-161): state_dict suffixes of (pre-norm gamma, up, conv, inner gamma, down).
+        # The plain FeedForward runs through the same fused kernels with the conv taps pinned to (0, 0, 1).
+        self.ffk = (dict(g1="2.0.gamma", w1="2.1.weight", conv="2.2.ds_conv.weight", gin="2.4.gamma", w2="2.6.weight") if self.use_conv_ff
+                    else dict(g1="2.0.gamma", w1="2.1.weight", conv=None, gin="2.3.gamma", w2="2.5.weight"))
+        self.F = int(self.d * 2 * 4 / 3) if self.use_conv_ff else int(self.d * 4)
         self.Fp = _round_up(self.F, 128)           # interleaved GEGLU layout: groups of 128 channels
         self.Hr = self.d // 2                      # rel-pos MLP width
         self.C = [s.codebook_size + 1 for s in self.seqs]
@@ -106,6 +124,7 @@ class Engine:
         self._build_arena()
         self._alloc_packed()
         self._packed_version = None
+        self.bwd_max_ctas = 0      # > 0: CTA cap of the backward GEMMs (data parallel: leaves SMs to the overlapped NCCL kernels)
         self._plans = {}
         self._ws = {}
         self.seed = torch.zeros(1, dtype=torch.int64, device=dev)      # dropout / forgetful-mask seed (device resident)
@@ -119,9 +138,10 @@ class Engine:
     # ------------------------------------------------------------------------------------------ arena
     def _build_arena(self):
         named = [(n, p) for n, p in self.m.named_parameters()]
-        emb = [(n, p) for n, p in named if n.startswith("embeddings.")]
+        is_row_table = lambda n: n.startswith("embeddings.") or n.startswith("absolute_position_embeddings.")
+        emb = [(n, p) for n, p in named if is_row_table(n)]
         start = [(n, p) for n, p in named if n.startswith("start_tokens.")]
-        decay = emb + [(n, p) for n, p in named if p.ndim >= 2 and not n.startswith("embeddings.")]
+        decay = emb + [(n, p) for n, p in named if p.ndim >= 2 and not is_row_table(n)]
         nodecay = start + [(n, p) for n, p in named if p.ndim < 2 and not n.startswith("start_tokens.")]
         off, layout = 0, {}
         for n, p in decay:
@@ -151,10 +171,10 @@ class Engine:
         self.arena_p, self.arena_g = arena_p, arena_g
         # embedding table = [embeddings.0 | embeddings.1 | ... ] rows of d floats; start tokens further down
         self.emb_off = emb_off
-        self.emb_row_base, r = [], 0
+        self.emb_row_base, self.abs_row_base = [], []
         for n, p in emb:
             assert (layout[n] - emb_off) % self.d == 0
-            self.emb_row_base.append((layout[n] - emb_off) // self.d)
+            (self.emb_row_base if n.startswith("embeddings.") else self.abs_row_base).append((layout[n] - emb_off) // self.d)
         self.start_row = [(layout[n] - emb_off) // self.d for n, _ in start]
         self.table = arena_p[emb_off:]
         self.dtable_emb = arena_g[emb_off:]
@@ -177,6 +197,10 @@ class Engine:
             for k in ("wq", "w1", "w2"):
                 pk[k + "_b"] = torch.empty_like(pk[k], dtype=bf) if dual else pk[k]
             self.pk.append(pk)
+        if not self.use_conv_ff:
+            for pk in self.pk:
+                pk["conv"].zero_()
+                pk["conv"][:, 2] = 1.0          # y[t] = u[t]: no depthwise conv in FeedForward (transformer.py:152-161)
         self.pk_logit = [torch.empty(s.num_quantizers, cp, d, device=dev, dtype=a16) for s, cp in zip(self.seqs, self.Cp)]
         self.pk_logit_b = [torch.empty_like(t, dtype=bf) if dual else t for t in self.pk_logit]
         self._pack_table = None
@@ -192,14 +216,16 @@ class Engine:
             tab = lib.PackTable(self.dev)
             for l, pk in enumerate(self.pk):
                 p = f"transformer.layers.{l}."
+                fk = self.ffk
                 for sfx in (("", "_b") if pk["wq"] is not pk["wq_b"] else ("",)):
                     tab.add(pv[p + "0.to_q.weight"], d, HD, d, pk["wq" + sfx], HD, d)
-                    tab.add(pv[p + "2.1.weight"], d, 2 * F, d, pk["w1" + sfx], 2 * Fp, d, split_dst=-1, split_src=F)
-                    tab.add(pv[p + "2.6.weight"], F, d, F, pk["w2" + sfx], d, Fp)
+                    tab.add(pv[p + fk["w1"]], d, 2 * F, d, pk["w1" + sfx], 2 * Fp, d, split_dst=-1, split_src=F)
+                    tab.add(pv[p + fk["w2"]], F, d, F, pk["w2" + sfx], d, Fp)
                 tab.add(pv[p + "0.to_kv.weight"], d, 128, d, pk["wkv_b"], 128, d)
                 tab.add(pv[p + "0.to_out.0.weight"], HD, d, HD, pk["wo_b"], d, HD)
-                tab.add(pv[p + "2.2.ds_conv.weight"], 3, 2 * F, 3, pk["conv"], 2 * Fp, 3, split_dst=-1, split_src=F)
-                tab.add(pv[p + "2.4.gamma"], F, 1, F, pk["gin"], 1, Fp)
+                if fk["conv"] is not None:
+                    tab.add(pv[p + fk["conv"]], 3, 2 * F, 3, pk["conv"], 2 * Fp, 3, split_dst=-1, split_src=F)
+                tab.add(pv[p + fk["gin"]], F, 1, F, pk["gin"], 1, Fp)
             for s, seq in enumerate(self.seqs):
                 # [q, C, d] -> [q, Cp, d]: every head padded with zero rows
                 for dst in ((self.pk_logit[s], self.pk_logit_b[s]) if self.pk_logit[s] is not self.pk_logit_b[s] else (self.pk_logit[s],)):
@@ -207,9 +233,16 @@ class Engine:
                             seq.num_quantizers * self.Cp[s], d, split_dst=self.Cp[s], split_src=self.C[s])
             self._pack_table = tab
         self._pack_table.run()
-        for j in (1, 2):
-            lib.split3_bf16(pv[f"transformer.rel_pos_bias.net.{j}.0.weight"], self.pk_rp[j - 1], weight_mode=True)
+        if self.bias_type == "continuous":
+            for j in (1, 2):
+                lib.split3_bf16(pv[f"transformer.rel_pos_bias.net.{j}.0.weight"], self.pk_rp[j - 1], weight_mode=True)
         self._packed_version = ver
+
+    def grad_bucket_plan(self, min_elems=4 << 20):
+        """All-reduce buckets of the gradient arena in backward-completion order (dist_utils.plan_buckets)."""
+        from .dist_utils import plan_buckets
+        sizes = {n: p.numel() for n, p in self.m.named_parameters()}
+        return plan_buckets(self.layout, sizes, self.n_params_arena, self.L, min_elems)
 
     def check_errors(self):
         """Raises if a token id outside an embedding table was seen since the last check (nn.Embedding's IndexError;
@@ -256,6 +289,10 @@ class Engine:
             ws.update(xn16=E(M, d, dt=a16), xn2_16=E(M, d, dt=a16), hn16=E(M, Fp, dt=a16),   # duplicates kept for backward
                       xf16=E(max(pl.rows_total, 1), d, dt=a16))
         lib.arange_f32(ws["rp_in"])
+        if self.bias_type == "none":
+            ws["table"].zero_()                 # no bias is added (transformer.py:372-373): written once, never touched again
+        elif self.bias_type == "t5":
+            ws["ones"] = torch.ones(pl.N, device=dev, dtype=f32)
         if train:
             ws.update(
                 dlogits=[E(max(pl.B * c, 1), self.Cp[s]) for (s, qi, c, b0) in pl.groups],
@@ -291,6 +328,24 @@ class Engine:
     def _bn(N):
         return 256 if N % 256 == 0 or N >= 2048 else 128
 
+    def build_bias_table(self, ws, N):
+        """table[h, delta] for delta = i - j in [0, N) of the configured relative position bias (transformer.py:366-373)."""
+        if self.bias_type == "continuous":
+            self._relpos_table(ws, N)
+        elif self.bias_type == "t5":
+            # T5RelativePositionBias (transformer.py:69-117) is fed i - j and negates it, so every causally visible pair
+            # falls into bucket 0: the table is the constant row 0 of the bucket embedding, one value per head
+            w = self.pview["transformer.rel_pos_bias.relative_attention_bias.weight"]       # [32, h]
+            lib.sgemm_small(w, (1, 1), ws["ones"], (1, 1), ws["table"], (ws["table"].stride(0), 1), self.h, N, 1)
+        # 'none': the table stays zero
+
+    def bias_table_backward(self, ws, N):
+        if self.bias_type == "continuous":
+            self._relpos_backward(ws, N)
+        elif self.bias_type == "t5":
+            gw = self.gview["transformer.rel_pos_bias.relative_attention_bias.weight"]      # bucket 0 collects every delta
+            lib.colsum(ws["dtable"], 1, ws["dtable"].stride(0), gw[0], N, self.h, accumulate=True)
+
     def _relpos_table(self, ws, N):
         """RelativePositionBias MLP on the causal distances 0..N-1 -> table[h, N] (transformer.py:55-67).
         The two Hr x Hr layers run on the tcgen05 GEMM with bf16x3-split operands (fp32-class accuracy: the
@@ -306,14 +361,15 @@ class Engine:
         # no split-K here: atomics would make the table, and through bf16 rounding every logit, depend on CTA timing
         lib.sgemm_small(ws["rp_a"][2], (Hr, 1), pv[pre + "3.weight"], (1, Hr), ws["table"], (1, N), N, h, Hr, bias=pv[pre + "3.bias"])
 
-    def forward_core(self, pl: _Plan, ws, src_row, key_mask, train: bool, groups_wanted=None, drop: bool = False):
-        """Runs embeddings -> depth x (attention, conv-FFN) -> final LN -> logit heads.  Activations stay in `ws`."""
+    def forward_core(self, pl: _Plan, ws, src_row, key_mask, train: bool, groups_wanted=None, drop: bool = False, capture=None):
+        """Runs embeddings -> depth x (attention, conv-FFN) -> final LN -> logit heads.  Activations stay in `ws`.
+        capture (decode.py): receives each layer's K/V rows and pre-conv FFN rows (the generation caches of the prompt)."""
         self.refresh_packed()
         B, N, M, d, h, HD, F, Fp = pl.B, pl.N, pl.M, self.d, self.h, self.HD, self.F, self.Fp
         pv = self.pview
         x = ws["x"]
-        lib.embed_gather(self.table, src_row, x[0])
-        self._relpos_table(ws, N)
+        lib.embed_gather(self.table, src_row, x[0], pl.src_row2)
+        self.build_bias_table(ws, N)
         drop_p = self.drop_p if drop else 0.0
         f16 = self.a16 != torch.bfloat16
         dup = f16 and train            # the backward pass needs bf16 duplicates of the fp16 forward operands
@@ -326,11 +382,15 @@ class Engine:
             lib.gemm(xn, pk["wq"], ws["q_raw"][i], block_n=self._bn_for(M, HD, d))
             lib.gemm(ws["xraw"][i], pk["wkv_b"], ws["kv_raw"][i], block_n=128)
             lib.qk_l2norm_fwd(ws["q_raw"][i], ws["kv_raw"][i], pv[p + "0.q_scale"], pv[p + "0.k_scale"], ws["qn"][i], ws["kvn"][i], h)
+            if capture is not None:
+                capture.after_kv(l, ws["kvn"][i])
             lib.attn_fwd_tc(ws["qn"][i], ws["kvn"][i], ws["table"], key_mask, ws["o"][i], ws["lse"][i], B, N, h)
             lib.gemm(ws["o"][i], pk["wo_b"], xm, addend=xa, block_n=self._bn_for(M, d, HD))
             xn2 = ws["xn2_16"] if f16 else ws["xn2"][i]
-            lib.layernorm_fwd(xm, pv[p + "2.0.gamma"], xn2, None, ws["st_f"][i], ycopy=ws["xn2"][i] if dup else None)
+            lib.layernorm_fwd(xm, pv[p + self.ffk["g1"]], xn2, None, ws["st_f"][i], ycopy=ws["xn2"][i] if dup else None)
             lib.gemm_ffn_up(xn2, pk["w1"], pk["conv"], ws["u"][i], ws["h"], ws["rowsum"], N, Fp)   # conv + GEGLU in the epilogue
+            if capture is not None:
+                capture.after_u(l, ws["u"][i])
             hn = ws["hn16"] if f16 else ws["hn"][i]
             lib.ffn_norm_fwd(ws["h"], ws["rowsum"], pk["gin"], hn, ws["st_i"][i], F, Fp, drop_p, self.seed, l,
                              keep_bits=ws["keep"][i] if drop_p > 0 else None, hn_copy=ws["hn"][i] if dup else None)
@@ -357,12 +417,15 @@ class Engine:
                     best = (c, bn, s)
         _, bn, s = best
         if s > 1:
-            lib.gemm(dy, x, gout, a_mn=True, b_mn=True, M=m, N=n, K=k, splits=s, block_n=bn, **kw)
+            lib.gemm(dy, x, gout, a_mn=True, b_mn=True, M=m, N=n, K=k, splits=s, block_n=bn, max_ctas=self.bwd_max_ctas, **kw)
         else:
-            lib.gemm(dy, x, gout, a_mn=True, b_mn=True, M=m, N=n, K=k, addend=gout, block_n=bn, **kw)
+            lib.gemm(dy, x, gout, a_mn=True, b_mn=True, M=m, N=n, K=k, addend=gout, block_n=bn, max_ctas=self.bwd_max_ctas, **kw)
 
-    def backward_core(self, pl: _Plan, ws, src_row, key_mask, groups_with_grad, drop: bool = False):
-        """Consumes ws['dlogits'] (bf16, permuted rows) and accumulates every parameter gradient into arena_g."""
+    def backward_core(self, pl: _Plan, ws, src_row, key_mask, groups_with_grad, drop: bool = False, on_ready=None):
+        """Consumes ws['dlogits'] (bf16, permuted rows) and accumulates every parameter gradient into arena_g.
+        on_ready(trigger): called when a group of gradients is final -- 'heads', 'layer<l>' (matrices of layer l), 'tail'
+        (everything else) -- so that a data-parallel caller can start reducing it underneath the rest of the pass."""
+        ready = on_ready if on_ready is not None else (lambda trigger: None)
         B, N, M, d, h, HD, F, Fp = pl.B, pl.N, pl.M, self.d, self.h, self.HD, self.F, self.Fp
         pv, gv = self.pview, self.gview
         x = ws["x"]
@@ -374,8 +437,9 @@ class Engine:
                 continue
             rows = B * cnt
             dl = ws["dlogits"][gi]
-            lib.gemm(dl, self.pk_logit_b[s][qi], ws["dxf"][base:base + rows], b_mn=True, M=rows, N=d, K=self.Cp[s], block_n=128)
+            lib.gemm(dl, self.pk_logit_b[s][qi], ws["dxf"][base:base + rows], b_mn=True, M=rows, N=d, K=self.Cp[s], block_n=128, max_ctas=self.bwd_max_ctas)
             self._wgrad(dl, ws["xf"][base:base + rows], gv[f"logit_weights.{s}"][qi], self.Cp[s], d, row_split=self.Cp[s], row_valid=self.C[s])
+        ready("heads")
         dxa, dxb = ws["dx"]
         lib.layernorm_bwd(ws["dxf"], x[2 * self.L], ws["st_o"], pv["transformer.norm.gamma"], dxa, gv["transformer.norm.gamma"],
                           src_row=pl.dest_row, dx_bf16=ws["dx_bf"])
@@ -384,33 +448,39 @@ class Engine:
             p, pk = f"transformer.layers.{l}.", self.pk[l]
             xa, xm = x[2 * l], x[2 * l + 1]
             # ---- conv feed-forward
-            lib.gemm(ws["dx_bf"], pk["w2_b"], ws["dhn"], b_mn=True, M=M, N=Fp, K=d, block_n=self._bn_for(M, Fp, d))
-            self._wgrad(ws["dx_bf"], ws["hn"][l], gv[p + "2.6.weight"], d, Fp, n_valid=F)
+            lib.gemm(ws["dx_bf"], pk["w2_b"], ws["dhn"], b_mn=True, M=M, N=Fp, K=d, block_n=self._bn_for(M, Fp, d), max_ctas=self.bwd_max_ctas)
+            fk = self.ffk
+            self._wgrad(ws["dx_bf"], ws["hn"][l], gv[p + fk["w2"]], d, Fp, n_valid=F)
             ws["dgin"].zero_(); ws["dconv"].zero_()
             lib.ffn_mid_bwd(ws["dhn"], ws["hn"][l], ws["u"][l], ws["st_i"][l], pk["conv"], pk["gin"], ws["rowstat"], ws["du"],
                             ws["dgin"], ws["dconv"], B, N, F, Fp, drop_p, keep_bits=ws["keep"][l] if drop_p > 0 else None)
-            lib.unpack_add(ws["dgin"], 1, Fp, gv[p + "2.4.gamma"], F, 1, F)
-            lib.unpack_add(ws["dconv"], 2 * Fp, 3, gv[p + "2.2.ds_conv.weight"], 3, 2 * F, 3, split_dst=-1, split_src=F)
-            lib.gemm(ws["du"], pk["w1_b"], ws["dxn"], b_mn=True, M=M, N=d, K=2 * Fp, block_n=self._bn_for(M, d, 2 * Fp))
-            self._wgrad(ws["du"], ws["xn2"][l], gv[p + "2.1.weight"], 2 * Fp, d, row_split=-1, row_valid=F)
-            lib.layernorm_bwd(ws["dxn"], xm, ws["st_f"][l], pv[p + "2.0.gamma"], dxb, gv[p + "2.0.gamma"], dres=dxa, dx_bf16=ws["dx_bf"])
+            lib.unpack_add(ws["dgin"], 1, Fp, gv[p + fk["gin"]], F, 1, F)
+            if fk["conv"] is not None:
+                lib.unpack_add(ws["dconv"], 2 * Fp, 3, gv[p + fk["conv"]], 3, 2 * F, 3, split_dst=-1, split_src=F)
+            lib.gemm(ws["du"], pk["w1_b"], ws["dxn"], b_mn=True, M=M, N=d, K=2 * Fp, block_n=self._bn_for(M, d, 2 * Fp), max_ctas=self.bwd_max_ctas)
+            self._wgrad(ws["du"], ws["xn2"][l], gv[p + fk["w1"]], 2 * Fp, d, row_split=-1, row_valid=F)
+            lib.layernorm_bwd(ws["dxn"], xm, ws["st_f"][l], pv[p + fk["g1"]], dxb, gv[p + fk["g1"]], dres=dxa, dx_bf16=ws["dx_bf"])
             # ---- attention
-            lib.gemm(ws["dx_bf"], pk["wo_b"], ws["d_o"], b_mn=True, M=M, N=HD, K=d, block_n=self._bn_for(M, HD, d))
+            lib.gemm(ws["dx_bf"], pk["wo_b"], ws["d_o"], b_mn=True, M=M, N=HD, K=d, block_n=self._bn_for(M, HD, d), max_ctas=self.bwd_max_ctas)
             self._wgrad(ws["dx_bf"], ws["o"][l], gv[p + "0.to_out.0.weight"], d, HD)
             ws["dqn"].zero_(); ws["dkvn"].zero_()
             lib.attn_bwd_tc(ws["qn"][l], ws["kvn"][l], ws["d_o"], ws["o"][l], ws["lse"][l], ws["table"], key_mask, ws["dsum"],
                             ws["dqn"], ws["dkvn"], ws["dtable"], B, N, h)
             lib.qk_l2norm_bwd(ws["dqn"], ws["dkvn"], ws["q_raw"][l], ws["kv_raw"][l], pv[p + "0.q_scale"], pv[p + "0.k_scale"],
                               ws["dq_raw"], ws["dkv_raw"], gv[p + "0.q_scale"], gv[p + "0.k_scale"], h)
-            lib.gemm(ws["dq_raw"], pk["wq_b"], ws["dxn"], b_mn=True, M=M, N=d, K=HD, block_n=self._bn_for(M, d, HD))
-            lib.gemm(ws["dkv_raw"], pk["wkv_b"], ws["dxraw"], b_mn=True, M=M, N=d, K=128, block_n=self._bn_for(M, d, 128))
+            lib.gemm(ws["dq_raw"], pk["wq_b"], ws["dxn"], b_mn=True, M=M, N=d, K=HD, block_n=self._bn_for(M, d, HD), max_ctas=self.bwd_max_ctas)
+            lib.gemm(ws["dkv_raw"], pk["wkv_b"], ws["dxraw"], b_mn=True, M=M, N=d, K=128, block_n=self._bn_for(M, d, 128), max_ctas=self.bwd_max_ctas)
             self._wgrad(ws["dq_raw"], ws["xn"][l], gv[p + "0.to_q.weight"], HD, d)
             self._wgrad(ws["dkv_raw"], ws["xraw"][l], gv[p + "0.to_kv.weight"], 128, d)
+            ready(f"layer{l}")
             lib.layernorm_bwd(ws["dxn"], xa, ws["st_a"][l], pv[p + "0.norm.gamma"], dxa, gv[p + "0.norm.gamma"], dres=dxb, draw=ws["dxraw"],
                               dx_bf16=ws["dx_bf"])
         # ---- embeddings + start tokens (grad_shrink: utils.py:60-61)
         lib.embed_scatter_add(self.dtable_emb, src_row, dxa, self.alpha)
-        self._relpos_backward(ws, N)
+        if pl.src_row2 is not None:
+            lib.embed_scatter_add(self.dtable_emb, pl.src_row2, dxa, self.alpha)
+        self.bias_table_backward(ws, N)
+        ready("tail")
 
     def _relpos_backward(self, ws, N):
         pv, gv, Hr, h = self.pview, self.gview, self.Hr, self.h

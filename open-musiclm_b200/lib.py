@@ -76,6 +76,10 @@ def device_check():
     call("omlm_device_check")
 
 
+def num_sms():
+    return int(load().omlm_num_sms())
+
+
 def gemm(a, b, out, *, a_mn=False, b_mn=False, M=None, N=None, K=None, addend=None, alpha=1.0,
          splits=1, row_split=0, row_valid=0, n_valid=0, block_n=128, max_ctas=0):
     """out[m,n] = alpha * sum_k A(m,k) B(n,k) (+ addend).  a: [M,K] (or [K,M] if a_mn); b: [N,K] (or [K,N] if b_mn).
@@ -134,9 +138,10 @@ def forgetful_mask(B, N, num_drop, seed_tensor, stream_id, device):
     return keep
 
 
-def embed_gather(table, src_row, x):
+def embed_gather(table, src_row, x, src_row2=None):
+    """x[m] = table[src_row[m]] (+ table[src_row2[m]]); negative rows contribute zero."""
     M, D = x.shape
-    call("omlm_embed_gather", _p(table), _p(src_row), _p(x), _I(M), _I(D), _stream())
+    call("omlm_embed_gather", _p(table), _p(src_row), _p(src_row2), _p(x), _I(M), _I(D), _stream())
 
 
 def embed_scatter_add(dtable, src_row, dx, scale):
@@ -298,3 +303,32 @@ class PackTable:
 def unpack_add(packed, rows_p, cols_p, dst, dst_ld, rows_valid, cols_valid, split_dst=0, split_src=0):
     call("omlm_unpack_add", _p(packed), _L(cols_p if packed.dim() == 1 else packed.stride(0)), _I(rows_p), _I(cols_p),
          _p(dst), _L(dst_ld), _I(rows_valid), _I(cols_valid), _I(split_dst), _I(split_src), _stream())
+
+
+# ------------------------------------------------------------------------------------------------ incremental decoding
+def skinny_gemm(A, W, out, *, prologue=0, gamma=None, rowsum=None, n_real=0, addend=None):
+    """out[b, n] = A[b, :] . W[n, :] (+ addend) for B <= 16 rows; prologue: see include/omlm_b200.h."""
+    B = A.shape[0]
+    N, K = W.shape
+    assert W.dtype in _T16 and W.stride(1) == 1 and out.stride(-1) == 1 and A.stride(-1) == 1
+    assert (prologue in (0, 3) and A.dtype == W.dtype) or (prologue in (1, 2) and A.dtype == torch.float32)
+    call("omlm_skinny_gemm", _p(A), _L(A.stride(0)), _I(prologue), _p(W), _L(W.stride(0)), _I(int(W.dtype == torch.float16)),
+         _p(gamma), _p(rowsum), _I(n_real), _p(addend), _L(addend.stride(0) if addend is not None else 0), _p(out),
+         _I(FMT[out.dtype]), _L(out.stride(0)), _I(B), _I(N), _I(K), _stream())
+
+
+def attn_decode(q_raw, kv_raw, q_scale, k_scale, cache, table, pos, max_pos, out, heads, scale=8.0):
+    call("omlm_attn_decode", _p(q_raw), _p(kv_raw), _p(q_scale), _p(k_scale), _p(cache), _L(cache.stride(0)), _p(table),
+         _I(table.stride(0)), _p(pos), _I(max_pos), _p(out), _I(q_raw.shape[0]), _I(heads), _F(scale), _stream())
+
+
+def decode_conv_geglu(u_new, state, conv_w, h_out, rowsum):
+    B, Fp2 = u_new.shape
+    assert u_new.dtype == state.dtype == h_out.dtype and u_new.dtype in _T16
+    call("omlm_decode_conv_geglu", _p(u_new), _p(state), _p(conv_w), _p(h_out), _p(rowsum), _I(B), _I(Fp2 // 2),
+         _I(int(u_new.dtype == torch.float16)), _stream())
+
+
+def sample(logits, C, top_k, temperature, allow_eos, uniform, seed, tokens, next_row, row_offset, counters, pos, B):
+    call("omlm_sample", _p(logits), _L(logits.stride(0)), _I(C), _I(top_k), _F(temperature), _I(int(allow_eos)), _p(uniform),
+         _p(seed), _p(tokens), _L(tokens.stride(0)), _p(next_row), _I(row_offset), _p(counters), _p(pos), _I(B), _stream())

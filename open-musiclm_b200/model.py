@@ -61,6 +61,19 @@ class _Attention(nn.Module):
         self.to_out = nn.ModuleList([_Weight(nn.Linear(inner, dim, bias=False).weight.detach()), nn.Identity()])
 
 
+def _feed_forward(dim):
+    """Parameter structure of the plain FeedForward, transformer.py:152-161 (GEGLU at index 2, Dropout at 4)."""
+    inner = int(dim * 4)
+    return nn.ModuleList([
+        _LayerNorm(dim),
+        _Weight(nn.Linear(dim, inner * 2, bias=False).weight.detach()),
+        nn.Identity(),
+        _LayerNorm(inner),
+        nn.Identity(),
+        _Weight(nn.Linear(inner, dim, bias=False).weight.detach()),
+    ])
+
+
 def _conv_feed_forward(dim):
     """Parameter structure of ConvFeedForward, transformer.py:140-150 (indices 3 and 5 hold no parameters)."""
     inner = int(dim * 2 * 4 / 3)
@@ -89,14 +102,28 @@ class _RelPosBias(nn.Module):
         self.net = nn.ModuleList(net)
 
 
+class _T5RelPosBias(nn.Module):
+    """T5RelativePositionBias, transformer.py:69-84: an Embedding(32 buckets, heads)."""
+    def __init__(self, heads, num_buckets=32):
+        super().__init__()
+        self.relative_attention_bias = _Weight(nn.Embedding(num_buckets, heads).weight.detach())
+
+
 class _Transformer(nn.Module):
     """Parameter structure of Transformer, transformer.py:338-383 (creation order = reference RNG order)."""
-    def __init__(self, dim, depth, heads):
+    def __init__(self, dim, depth, heads, use_conv_ff=True, relative_position_bias_type="continuous"):
         super().__init__()
         self.layers = nn.ModuleList([])
-        self.rel_pos_bias = _RelPosBias(dim // 2, heads)
+        if relative_position_bias_type == "continuous":
+            self.rel_pos_bias = _RelPosBias(dim // 2, heads)
+        elif relative_position_bias_type == "t5":
+            self.rel_pos_bias = _T5RelPosBias(heads)
+        elif relative_position_bias_type == "none":
+            self.rel_pos_bias = None
+        else:
+            raise ValueError(f"invalid relative position bias type: {relative_position_bias_type}")
         for _ in range(depth):
-            self.layers.append(nn.ModuleList([_Attention(dim, heads), None, _conv_feed_forward(dim)]))
+            self.layers.append(nn.ModuleList([_Attention(dim, heads), None, _conv_feed_forward(dim) if use_conv_ff else _feed_forward(dim)]))
         self.norm = _LayerNorm(dim)
 
 
@@ -112,14 +139,10 @@ class TokenConditionedTransformer(nn.Module):
         unsupported = []
         if has_condition or cond_as_self_attn_prefix:
             unsupported.append("has_condition / cond_as_self_attn_prefix (dead in every shipped config)")
-        if use_absolute_position_embeddings:
-            unsupported.append("use_absolute_position_embeddings=True")
-        if not kwargs.get("use_conv_ff", True):
-            unsupported.append("use_conv_ff=False")
         if kwargs.get("non_causal_prefix_size", 0) != 0:
             unsupported.append("non_causal_prefix_size>0")
-        if kwargs.get("relative_position_bias_type", "continuous") != "continuous":
-            unsupported.append("relative_position_bias_type != 'continuous'")
+        if kwargs.get("relative_position_bias_type", "continuous") not in ("continuous", "t5", "none"):
+            raise ValueError(f"invalid relative position bias type: {kwargs.get('relative_position_bias_type')}")
         if kwargs.get("use_memory_efficient_attention", False):
             unsupported.append("use_memory_efficient_attention=True (xformers)")
         if attn_dropout != 0.:
@@ -136,11 +159,14 @@ class TokenConditionedTransformer(nn.Module):
         self.dim, self.depth, self.heads = dim, depth, heads
         self.ff_dropout = ff_dropout
         self.grad_shrink_alpha = grad_shrink_alpha
+        self.use_conv_ff = bool(kwargs.get("use_conv_ff", True))
+        self.relative_position_bias_type = kwargs.get("relative_position_bias_type", "continuous")
+        self.max_absolute_position_embeddings = max_absolute_position_embeddings
 
         self.start_tokens = nn.ParameterList()
         self.logit_weights = nn.ParameterList()
         self.embeddings = nn.ModuleList()
-        self.absolute_position_embeddings = None
+        self.absolute_position_embeddings = nn.ModuleList() if use_absolute_position_embeddings else None
         self.eos_ids = []
         for seq in token_sequences:   # same RNG consumption order as open_musiclm.py:72-82
             self.start_tokens.append(nn.Parameter(torch.randn(dim)))
@@ -148,7 +174,9 @@ class TokenConditionedTransformer(nn.Module):
             cb = seq.codebook_size + 1
             self.embeddings.append(_Weight(nn.Embedding(cb * seq.num_quantizers, dim).weight.detach()))
             self.logit_weights.append(nn.Parameter(torch.randn(seq.num_quantizers, cb, dim)))
-        self.transformer = _Transformer(dim, depth, heads)
+            if use_absolute_position_embeddings:
+                self.absolute_position_embeddings.append(_Weight(nn.Embedding(max_absolute_position_embeddings, dim).weight.detach()))
+        self.transformer = _Transformer(dim, depth, heads, self.use_conv_ff, self.relative_position_bias_type)
         self._engine = None
 
     # ------------------------------------------------------------------ plumbing

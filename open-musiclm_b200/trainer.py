@@ -14,13 +14,14 @@ Semantics kept from the reference:
     arena after the last micro-batch, the 1/world factor folded into the clip/AdamW kernel
     (the reference all-reduces on every micro-batch; the reduced result is identical).
 """
+import os
 from typing import List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
 
 from . import lib
-from .dist_utils import allreduce_sum_, grad_prescale, rank_seed, world_info
+from .dist_utils import BucketReducer, allreduce_sum_, grad_prescale, rank_seed, world_info
 from .model import TokenConditionedTransformer
 
 
@@ -69,12 +70,23 @@ class HotPathTrainer:
         self._mask_draws = 0
         self.use_cuda_graph = use_cuda_graph
         self._graphs = {}
+        # data parallel: bucketed gradient all-reduce on a side stream underneath the backward pass.  The
+        # persistent GEMMs schedule their tiles statically, so during the overlapped backward they leave `nccl_ctas` SMs
+        # to the NCCL kernels (NCCL_MAX_CTAS is set to the same number before the communicator is created, see bench.py)
+        self.reducer = None
+        self.allreduce_mode = "none (single GPU)"
+        if self.world > 1:
+            self.reducer = BucketReducer(eng.arena_g, eng.grad_bucket_plan(), process_group, side_stream=torch.cuda.Stream())
+            nccl_ctas = int(os.environ.get("NCCL_MAX_CTAS", "0") or 0)
+            eng.bwd_max_ctas = max(1, lib.num_sms() - nccl_ctas) if nccl_ctas > 0 else 0
+            self.allreduce_mode = (f"{len(self.reducer.order)} buckets in backward order on a side stream, overlapped with the backward pass"
+                                   + (f"; backward GEMMs on {eng.bwd_max_ctas} CTAs, NCCL on <= {nccl_ctas}" if nccl_ctas else ""))
         self.loss_out = torch.zeros((), device=eng.dev)
         self._loss_ring = None
         eng.arena_g.zero_()
 
     # -------------------------------------------------------------------------------------------
-    def _micro_batch(self, token_ids: Sequence[torch.Tensor], train: bool, slot: int, backward: bool):
+    def _micro_batch(self, token_ids: Sequence[torch.Tensor], train: bool, slot: int, backward: bool, reducer=None):
         eng = self.eng
         dev = eng.dev
         ids = [t.reshape(t.shape[0], -1).to(dev, torch.int64, non_blocking=True) for t in token_ids]
@@ -120,7 +132,7 @@ class HotPathTrainer:
         loss = torch.stack(loss_parts).sum()
         self.loss_buf[slot] = loss
         if backward:
-            eng.backward_core(pl, ws, src_row, key_mask, weighted, drop)
+            eng.backward_core(pl, ws, src_row, key_mask, weighted, drop, on_ready=reducer.fire if reducer is not None else None)
         return loss
 
     def _set_hyper(self):
@@ -136,10 +148,19 @@ class HotPathTrainer:
         h[8] = grad_prescale(self.pg)
         self.hyper.copy_(h, non_blocking=True)
 
-    def _fwd_bwd_body(self, micro_batches):
-        """Device work of one optimiser step up to the gradient arena (capturable in a CUDA graph)."""
+    def _fwd_bwd_body(self, micro_batches, overlap=True):
+        """Device work of one optimiser step up to the reduced gradient arena (capturable in a CUDA graph).  With several
+        ranks the last micro-batch's backward pass fires the bucketed all-reduces (the reference reduces on every
+        micro-batch, trainer.py:439; the reduced sum is the same)."""
+        red = self.reducer if overlap else None
+        if red is not None:
+            red.begin()
         for i, mb in enumerate(micro_batches):
-            self._micro_batch(mb, True, i, True)
+            self._micro_batch(mb, True, i, True, reducer=red if i == len(micro_batches) - 1 else None)
+        if red is not None:
+            red.join()
+        elif self.world > 1:
+            allreduce_sum_(self.eng.arena_g, self.pg)
 
     def _update_body(self):
         """Clip + AdamW + re-pack on the (already all-reduced) gradient arena (capturable in a CUDA graph)."""
@@ -154,20 +175,61 @@ class HotPathTrainer:
 
     def _step_body(self, micro_batches):
         self._fwd_bwd_body(micro_batches)
-        allreduce_sum_(self.eng.arena_g, self.pg)
         self._update_body()
+
+    def _capture(self, st):
+        """One CUDA graph for the whole step.  With several ranks the NCCL all-reduces are captured too (fork / join on
+        the side stream; thread-local capture mode keeps NCCL's watchdog thread out of it).  If that capture is refused,
+        fall back to two graphs around ONE eager all-reduce of the arena (no overlap)."""
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.pg)
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._step_body(st["static"])
+            return ("one", g)
+        except Exception as e:
+            import warnings
+            torch.cuda.synchronize()
+            if self.world == 1:
+                warnings.warn(f"CUDA graph capture of the training step failed ({e}); continuing with eager launches")
+                return None
+            warnings.warn(f"CUDA graph capture with NCCL failed ({e}); using two graphs around one eager all-reduce")
+        try:
+            self.allreduce_mode = "one eager all-reduce of the arena between two CUDA graphs (not overlapped)"
+            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga):
+                for i, mb in enumerate(st["static"]):
+                    self._micro_batch(mb, True, i, True)
+            with torch.cuda.graph(gb, pool=ga.pool()):
+                self._update_body()
+            return ("two", ga, gb)
+        except Exception as e:
+            import warnings
+            warnings.warn(f"CUDA graph capture of the training step failed ({e}); continuing with eager launches")
+            torch.cuda.synchronize()
+            return None
+
+    def _replay(self, graphs):
+        if graphs[0] == "one":
+            graphs[1].replay()
+        else:
+            graphs[1].replay()
+            allreduce_sum_(self.eng.arena_g, self.pg)
+            graphs[2].replay()
 
     def train_step(self, micro_batches: Sequence[Sequence[torch.Tensor]]):
         """One optimiser step over `grad_accum_every` micro-batches (each a tuple of token-id tensors in
         the stage's order, e.g. (clap, semantic, coarse); host or device).  Returns the mean loss as a device
-        scalar.  After two eager steps per input shape the step is replayed from two CUDA graphs (forward+backward,
-        ~300 kernels; clip+AdamW+re-pack) with the NCCL gradient all-reduce launched eagerly between them; inputs are
-        copied into static device buffers, hyper-parameters live in device memory."""
+        scalar.  After two eager steps per input shape the step is replayed from ONE CUDA graph (forward, backward, the
+        bucketed NCCL all-reduces on their side stream, clip, AdamW, re-pack); inputs are copied into static device
+        buffers, hyper-parameters live in device memory."""
         assert len(micro_batches) == self.grad_accum_every
         eng = self.eng
         self.transformer.train()
         eng.refresh_packed()        # no-op unless the parameters were written from outside (load_state_dict, manual edits):
-        self._set_hyper()           # the captured graphs re-pack only after their own optimiser update
+        self._set_hyper()           # the captured graph re-packs only after its own optimiser update
         if not self.use_cuda_graph:
             self._step_body(micro_batches)
             self.steps += 1
@@ -181,31 +243,17 @@ class HotPathTrainer:
             for t, sbuf in zip(mb, smb):
                 sbuf.copy_(t, non_blocking=True)
         if st["graphs"] is not None:
-            st["graphs"][0].replay()
-            allreduce_sum_(eng.arena_g, self.pg)
-            st["graphs"][1].replay()
+            self._replay(st["graphs"])
         elif st["count"] < 2:
             self._step_body(st["static"])
             st["count"] += 1
         else:
-            torch.cuda.synchronize()
-            try:
-                ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-                with torch.cuda.graph(ga):
-                    self._fwd_bwd_body(st["static"])
-                with torch.cuda.graph(gb, pool=ga.pool()):
-                    self._update_body()
-                st["graphs"] = (ga, gb)
-            except Exception as e:  # capture not possible in this environment: stay on the eager launch path (same kernels)
-                import warnings
-                warnings.warn(f"CUDA graph capture of the training step failed ({e}); continuing with eager launches")
+            st["graphs"] = self._capture(st)
+            if st["graphs"] is None:
                 self.use_cuda_graph = False
-                torch.cuda.synchronize()
                 self._step_body(st["static"])
             else:
-                ga.replay()
-                allreduce_sum_(eng.arena_g, self.pg)
-                gb.replay()
+                self._replay(st["graphs"])
         self.steps += 1
         return self.loss_out
 

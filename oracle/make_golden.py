@@ -32,6 +32,16 @@ CASES = {
     "tiny_fine": ("fine", dict(dim=64, depth=1, heads=3, clap_codebook_size=64, acoustic_codebook_size=64,
                                num_clap_quantizers=4, num_coarse_quantizers=3, num_fine_quantizers=5),
                   [(2, 4), (2, 6, 3), (2, 23)], [1.0, 1.0, 1.0]),
+    # configuration variants: plain GEGLU FeedForward (transformer.py:152-161) + T5 bias (69-117);
+    # no relative bias + per-sequence absolute position embeddings (open_musiclm.py:81-82,134-136)
+    "tiny_plainff_t5": ("coarse", dict(dim=64, depth=2, heads=2, clap_codebook_size=64, semantic_codebook_size=64,
+                                       acoustic_codebook_size=64, num_clap_quantizers=4, num_coarse_quantizers=3,
+                                       use_conv_ff=False, relative_position_bias_type="t5"),
+                        [(2, 4), (2, 9), (2, 7, 3)], [0.0, 0.0, 1.0]),
+    "tiny_nobias_abspos": ("semantic", dict(dim=64, depth=2, heads=2, clap_codebook_size=64, semantic_codebook_size=64,
+                                            num_clap_quantizers=4, relative_position_bias_type="none",
+                                            use_absolute_position_embeddings=True),
+                           [(2, 4), (2, 27)], [1.0, 1.0]),
 }
 COMMON = dict(attn_dropout=0.0, ff_dropout=0.1, grad_shrink_alpha=0.1, non_causal_prefix_size=0,
               relative_position_bias_type="continuous", use_memory_efficient_attention=False)
@@ -40,13 +50,16 @@ COMMON = dict(attn_dropout=0.0, ff_dropout=0.1, grad_shrink_alpha=0.1, non_causa
 def build(ref, stage, kw):
     fn = {"semantic": ref.create_semantic_transformer, "coarse": ref.create_coarse_transformer,
           "fine": ref.create_fine_transformer}[stage]
-    return fn(**kw, **COMMON)
+    return fn(**dict(COMMON, **kw))
 
 
 def main():
     ref = ref_harness.import_reference()
     os.makedirs(GOLD, exist_ok=True)
+    only = set(sys.argv[1:])
     for name, (stage, kw, shapes, cew) in CASES.items():
+        if only and name not in only:
+            continue
         torch.manual_seed(0)
         model = build(ref, stage, kw)
         # perturb the unit-initialised parameters so that parity tests see non-trivial gammas / scales
@@ -75,7 +88,7 @@ def main():
             masks.append(torch.nn.functional.pad(m, (1, 0), value=True))
         masks.append(torch.ones(ids[-1].shape[0], ids[-1].shape[1] + 1, dtype=torch.bool))
         fx = {
-            "stage": stage, "kwargs": dict(kw, **COMMON), "ce_weights": cew,
+            "stage": stage, "kwargs": dict(COMMON, **kw), "ce_weights": cew,
             "state_dict": {k: v.detach().clone() for k, v in model.state_dict().items()},
             "tokens": tokens, "ids": ids, "key_mask": torch.cat(masks, 1),
             "labels": labels, "logits": [l.detach().permute(0, 2, 1).contiguous() for l in logits],  # back to [b, n, c]

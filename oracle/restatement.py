@@ -40,10 +40,23 @@ class Cfg:
     ce_weights: Optional[List[float]] = None
     mask_prob: float = 0.15                 # open_musiclm.py:228
     pad_id: int = -1
+    use_conv_ff: bool = True                # transformer.py:349, 380: ConvFeedForward vs FeedForward
+    rel_pos_bias_type: str = "continuous"   # transformer.py:353, 366-373: 'continuous' | 't5' | 'none'
+    abs_pos: bool = False                   # open_musiclm.py:53-54, 81-82, 134-136: per-sequence absolute position embeddings
+    max_abs_pos: int = 262
 
     @property
     def ff_inner(self) -> int:
+        if not self.use_conv_ff:
+            return int(self.dim * 4)        # transformer.py:153
         return int(self.dim * 2 * 4 / 3)    # transformer.py:141
+
+    @property
+    def ff_keys(self):
+        """state_dict suffixes of the feed-forward Sequential: (pre-norm gamma, up weight, conv weight or None, inner gamma, down weight)."""
+        if self.use_conv_ff:
+            return ("0.gamma", "1.weight", "2.ds_conv.weight", "4.gamma", "6.weight")     # transformer.py:142-150
+        return ("0.gamma", "1.weight", None, "3.gamma", "5.weight")                       # transformer.py:154-161
 
 
 def semantic_cfg(dim=1024, depth=6, heads=8, codebook=1024, n_clap_q=12, **kw) -> Cfg:
@@ -84,14 +97,19 @@ def init_state(cfg: Cfg, seed: int = 0) -> Dict[str, torch.Tensor]:
         sd[f"start_tokens.{i}"] = torch.randn(d, generator=g)
         sd[f"logit_weights.{i}"] = torch.randn(s.num_quantizers, s.codebook_size + 1, d, generator=g)
         sd[f"embeddings.{i}.weight"] = torch.randn((s.codebook_size + 1) * s.num_quantizers, d, generator=g)
+        if cfg.abs_pos:
+            sd[f"absolute_position_embeddings.{i}.weight"] = torch.randn(cfg.max_abs_pos, d, generator=g)
     hid = d // 2                                    # transformer.py:367
-    sd["transformer.rel_pos_bias.net.0.0.weight"] = lin(hid, 1)
-    sd["transformer.rel_pos_bias.net.0.0.bias"] = (torch.rand(hid, generator=g) * 2 - 1)
-    for j in (1, 2):
-        sd[f"transformer.rel_pos_bias.net.{j}.0.weight"] = lin(hid, hid)
-        sd[f"transformer.rel_pos_bias.net.{j}.0.bias"] = (torch.rand(hid, generator=g) * 2 - 1) / math.sqrt(hid)
-    sd["transformer.rel_pos_bias.net.3.weight"] = lin(h, hid)
-    sd["transformer.rel_pos_bias.net.3.bias"] = (torch.rand(h, generator=g) * 2 - 1) / math.sqrt(hid)
+    if cfg.rel_pos_bias_type == "continuous":
+        sd["transformer.rel_pos_bias.net.0.0.weight"] = lin(hid, 1)
+        sd["transformer.rel_pos_bias.net.0.0.bias"] = (torch.rand(hid, generator=g) * 2 - 1)
+        for j in (1, 2):
+            sd[f"transformer.rel_pos_bias.net.{j}.0.weight"] = lin(hid, hid)
+            sd[f"transformer.rel_pos_bias.net.{j}.0.bias"] = (torch.rand(hid, generator=g) * 2 - 1) / math.sqrt(hid)
+        sd["transformer.rel_pos_bias.net.3.weight"] = lin(h, hid)
+        sd["transformer.rel_pos_bias.net.3.bias"] = (torch.rand(h, generator=g) * 2 - 1) / math.sqrt(hid)
+    elif cfg.rel_pos_bias_type == "t5":
+        sd["transformer.rel_pos_bias.relative_attention_bias.weight"] = torch.randn(32, h, generator=g)
     for l in range(cfg.depth):
         p = f"transformer.layers.{l}."
         sd[p + "0.q_scale"] = torch.ones(dh)
@@ -101,13 +119,15 @@ def init_state(cfg: Cfg, seed: int = 0) -> Dict[str, torch.Tensor]:
         sd[p + "0.to_q.weight"] = lin(h * dh, d)
         sd[p + "0.to_kv.weight"] = lin(2 * dh, d)
         sd[p + "0.to_out.0.weight"] = lin(d, h * dh)
-        sd[p + "2.0.gamma"] = torch.ones(d)
-        sd[p + "2.0.beta"] = torch.zeros(d)
-        sd[p + "2.1.weight"] = lin(2 * F_, d)
-        sd[p + "2.2.ds_conv.weight"] = ((torch.rand(2 * F_, 1, 3, generator=g) * 2 - 1) / math.sqrt(3.0))
-        sd[p + "2.4.gamma"] = torch.ones(F_)
-        sd[p + "2.4.beta"] = torch.zeros(F_)
-        sd[p + "2.6.weight"] = lin(d, F_)
+        k_g1, k_w1, k_conv, k_gin, k_w2 = cfg.ff_keys
+        sd[p + "2." + k_g1] = torch.ones(d)
+        sd[p + "2." + k_g1.replace("gamma", "beta")] = torch.zeros(d)
+        sd[p + "2." + k_w1] = lin(2 * F_, d)
+        if k_conv is not None:
+            sd[p + "2." + k_conv] = ((torch.rand(2 * F_, 1, 3, generator=g) * 2 - 1) / math.sqrt(3.0))
+        sd[p + "2." + k_gin] = torch.ones(F_)
+        sd[p + "2." + k_gin.replace("gamma", "beta")] = torch.zeros(F_)
+        sd[p + "2." + k_w2] = lin(d, F_)
     sd["transformer.norm.gamma"] = torch.ones(d)
     sd["transformer.norm.beta"] = torch.zeros(d)
     return sd
@@ -180,10 +200,28 @@ def layer_norm(x, gamma):
     return (x - mu) * torch.rsqrt(var + 1e-5) * gamma
 
 
-def rel_pos_table(sd, n: int) -> torch.Tensor:
+def t5_bucket(relative_position: torch.Tensor, num_buckets=32, max_distance=128) -> torch.Tensor:
+    """T5RelativePositionBias._relative_position_bucket (causal), transformer.py:86-104.  NB: it is fed i - j and negates
+    it (n = j - i, clamped at 0), so every causally visible pair (j <= i) lands in bucket 0."""
+    n = torch.max(-relative_position, torch.zeros_like(relative_position))
+    max_exact = num_buckets // 2
+    is_small = n < max_exact
+    val_if_large = max_exact + (torch.log(n.float() / max_exact) / math.log(max_distance / max_exact) * (num_buckets - max_exact)).long()
+    val_if_large = torch.min(val_if_large, torch.full_like(val_if_large, num_buckets - 1))
+    return torch.where(is_small, n, val_if_large)
+
+
+def rel_pos_table(sd, n: int, bias_type: str = "continuous", heads: int = 0) -> torch.Tensor:
     """RelativePositionBias.forward, transformer.py:55-67, restricted to the causal side: returns
     table[h, delta] for delta = i - j in [0, n).  (The reference evaluates the MLP on all 2n-1
-    distances and gathers [h, i, j]; entries with j > i are overwritten by the causal mask.)"""
+    distances and gathers [h, i, j]; entries with j > i are overwritten by the causal mask.)
+    't5': T5RelativePositionBias.forward, transformer.py:106-117 (bucket of i - j, see t5_bucket); 'none': zeros
+    (transformer.py:372-373: no bias is added)."""
+    if bias_type == "none":
+        return torch.zeros(heads, n)
+    if bias_type == "t5":
+        bucket = t5_bucket(torch.arange(n))                        # delta = i - j >= 0
+        return sd["transformer.rel_pos_bias.relative_attention_bias.weight"][bucket].t().contiguous()
     x = torch.arange(n, dtype=torch.float32)[:, None]
     for j in range(3):
         x = F.silu(x @ sd[f"transformer.rel_pos_bias.net.{j}.0.weight"].t() + sd[f"transformer.rel_pos_bias.net.{j}.0.bias"])
@@ -219,20 +257,23 @@ def attention(cfg: Cfg, sd, p: str, x, table, key_mask):
 
 
 def conv_feed_forward(cfg: Cfg, sd, p: str, x, drop_keep=None):
-    """ConvFeedForward, transformer.py:140-150 (CausalDSConv 122-131, GEGLU 134-137).
+    """ConvFeedForward, transformer.py:140-150 (CausalDSConv 122-131, GEGLU 134-137), or the plain FeedForward
+    (transformer.py:152-161: same chain without the depthwise conv, inner width 4 d) when cfg.use_conv_ff is False.
     drop_keep: optional [B, N, F] boolean keep-mask for the inner dropout (training)."""
     Fi = cfg.ff_inner
-    xn = layer_norm(x, sd[p + "0.gamma"])
-    u = xn @ sd[p + "1.weight"].t()                                                             # :144
-    w = sd[p + "2.ds_conv.weight"][:, 0, :]                                                     # [2F, 3]
-    up = F.pad(u, (0, 0, 2, 0))                                                                 # left-pad time by 2 (:129)
-    y = up[:, 0:-2] * w[:, 0] + up[:, 1:-1] * w[:, 1] + up[:, 2:] * w[:, 2]                     # :130
+    k_g1, k_w1, k_conv, k_gin, k_w2 = cfg.ff_keys
+    xn = layer_norm(x, sd[p + k_g1])
+    y = xn @ sd[p + k_w1].t()                                                                   # :144 / :156
+    if k_conv is not None:
+        w = sd[p + k_conv][:, 0, :]                                                             # [2F, 3]
+        up = F.pad(y, (0, 0, 2, 0))                                                             # left-pad time by 2 (:129)
+        y = up[:, 0:-2] * w[:, 0] + up[:, 1:-1] * w[:, 1] + up[:, 2:] * w[:, 2]                 # :130
     a, g = y[..., :Fi], y[..., Fi:]                                                             # :136
     hmid = F.gelu(g) * a                                                                        # :137 (exact erf)
-    hn = layer_norm(hmid, sd[p + "4.gamma"])                                                    # :147
+    hn = layer_norm(hmid, sd[p + k_gin])                                                        # :147 / :158
     if drop_keep is not None:
-        hn = hn * drop_keep / (1.0 - cfg.ff_dropout)                                            # :148
-    return hn @ sd[p + "6.weight"].t()                                                          # :149
+        hn = hn * drop_keep / (1.0 - cfg.ff_dropout)                                            # :148 / :159
+    return hn @ sd[p + k_w2].t()                                                                # :149 / :160
 
 
 def transformer_trunk(cfg: Cfg, sd, x, key_mask, drop_keeps=None):
@@ -240,7 +281,7 @@ def transformer_trunk(cfg: Cfg, sd, x, key_mask, drop_keeps=None):
     N = x.shape[1]
     a = cfg.grad_shrink_alpha
     x = x * a + x.detach() * (1 - a)                                                            # :400, utils.py:60-61
-    table = rel_pos_table(sd, N)                                                                # :405
+    table = rel_pos_table(sd, N, cfg.rel_pos_bias_type, cfg.heads)                              # :402-405
     for l in range(cfg.depth):
         p = f"transformer.layers.{l}."
         x = attention(cfg, sd, p + "0.", x, table, key_mask) + x                                # :415
@@ -255,6 +296,8 @@ def embed(cfg: Cfg, sd, ids: Sequence[np.ndarray]) -> torch.Tensor:
     for s, (rows, pad) in enumerate(embedding_rows(cfg, ids)):
         e = sd[f"embeddings.{s}.weight"][torch.from_numpy(rows)]
         e = e.masked_fill(torch.from_numpy(pad)[..., None], 0.0)                                # utils.py:137-138
+        if cfg.abs_pos:                                                                         # open_musiclm.py:134-136
+            e = e + sd[f"absolute_position_embeddings.{s}.weight"][:e.shape[1]][None]
         parts.append(sd[f"start_tokens.{s}"][None, None, :].expand(B, 1, -1))
         parts.append(e)
     return torch.cat(parts, 1)
@@ -346,3 +389,71 @@ def clip_and_adamw(params: Dict[str, torch.Tensor], grads: Dict[str, torch.Tenso
         denom = (st["v"].sqrt() / math.sqrt(1 - b2 ** t)).add_(eps)
         params[k].addcdiv_(st["m"], denom, value=-cur_lr / (1 - b1 ** t))
     return total
+
+
+# --------------------------------------------------------------------------------------------
+# autoregressive generation (TokenConditionedTransformerWrapper.generate, open_musiclm.py:253-326)
+# --------------------------------------------------------------------------------------------
+
+def top_k_filter(logits: torch.Tensor, thres: float) -> torch.Tensor:
+    """utils.py:78-84: keep the k = max(int((1 - thres) * C), 1) largest logits, -inf elsewhere."""
+    k = max(int((1 - thres) * logits.shape[-1]), 1)
+    val, ind = torch.topk(logits, k)
+    out = torch.full_like(logits, float("-inf"))
+    out.scatter_(1, ind, val)
+    return out
+
+
+def gumbel_argmax(logits: torch.Tensor, uniform: torch.Tensor, temperature: float) -> torch.Tensor:
+    """utils.py:71-76 given the uniform(0,1) draw: argmax(logits / T - log(-log(u + 1e-20) + 1e-20))."""
+    noise = -torch.log(-torch.log(uniform + 1e-20) + 1e-20)
+    return (logits / temperature + noise).argmax(dim=-1)
+
+
+def generate(cfg: Cfg, sd, conditioning_token_ids: Sequence[np.ndarray], uniforms, pred_token_ids: Optional[np.ndarray] = None,
+             max_time_steps=8, filter_thres=0.9, temperature=1.0, include_eos_in_output=False, allow_eos_in_output=False,
+             return_trace=False):
+    """TokenConditionedTransformerWrapper.generate, open_musiclm.py:253-326, for unique_consecutive=False sequences:
+    eos appended to every conditioning sequence (:288-290; ids are NOT zeroed and there is NO key mask at inference),
+    the full prefix is re-run for every new token (:303-307), eos is forbidden except at the last quantizer of a time
+    step when allow_eos_in_output (:311-313), top-k (utils.py:78-84) then Gumbel-argmax (utils.py:71-76), finally
+    everything after an eos is set to -1 (:321-322, utils.py:86-93) and the flat ids are folded to [b, n, q] (:323-324).
+    `uniforms(step, shape)` supplies the uniform(0,1) draw of gumbel_noise for each sampled token, in order.
+    return_trace: also return per-step (logits of the last position, gap between the best and second-best noisy score)."""
+    S = len(cfg.seqs)
+    assert len(conditioning_token_ids) == S - 1
+    B = conditioning_token_ids[0].shape[0]
+    cond = [np.asarray(t).reshape(B, -1).astype(np.int64) for t in conditioning_token_ids]
+    cond = [np.concatenate([t, np.full((B, 1), s.codebook_size, np.int64)], 1) for t, s in zip(cond, cfg.seqs)]   # :288-290
+    info = cfg.seqs[-1]
+    eos = info.codebook_size
+    if pred_token_ids is not None:
+        init_step = pred_token_ids.shape[1]                                                                        # :276
+        pred = np.asarray(pred_token_ids).reshape(B, -1).astype(np.int64)
+    else:
+        init_step = 0
+        pred = np.zeros((B, 0), np.int64)
+    trace = []
+    step = 0
+    with torch.no_grad():
+        for _t in range(init_step, max_time_steps):
+            for ind in range(info.num_quantizers):
+                last = ind == info.num_quantizers - 1
+                lg = forward_logits(cfg, sd, cond + [pred], None, only_final=True)[-1][:, -1].clone()             # :303-309
+                if not allow_eos_in_output or not last:
+                    lg[:, -1] = float("-inf")                                                                      # :311-313
+                filt = top_k_filter(lg, filter_thres)
+                u = uniforms(step, tuple(filt.shape))
+                noisy = filt / temperature + (-torch.log(-torch.log(u + 1e-20) + 1e-20))
+                top2 = torch.topk(noisy, 2, dim=-1).values
+                sampled = noisy.argmax(dim=-1)
+                trace.append((lg, (top2[:, 0] - top2[:, 1]).clone()))
+                pred = np.concatenate([pred, sampled.numpy()[:, None]], 1)                                          # :318-319
+                step += 1
+    out = torch.from_numpy(pred)
+    eos_mask = (out == eos).float()
+    if include_eos_in_output:
+        eos_mask = F.pad(eos_mask, (1, -1))                                                                        # utils.py:89-90
+    out = out.masked_fill(eos_mask.cumsum(-1) > 0, -1)
+    out = out.view(B, -1, info.num_quantizers)
+    return (out, trace) if return_trace else out

@@ -48,15 +48,19 @@ def test_init_is_bit_identical_to_reference_under_same_seed():
     if not ref_harness.available():
         pytest.skip("reference tree not present")
     ref = ref_harness.import_reference()
-    kw = dict(dim=128, depth=2, heads=2, attn_dropout=0.0, ff_dropout=0.1)
-    for mine, theirs in [(O.create_semantic_transformer, ref.create_semantic_transformer),
-                         (O.create_coarse_transformer, ref.create_coarse_transformer),
-                         (O.create_fine_transformer, ref.create_fine_transformer)]:
-        torch.manual_seed(0); a = mine(**kw).state_dict()
-        torch.manual_seed(0); b = theirs(**kw).state_dict()
-        assert list(a.keys()) == list(b.keys())
-        for k in a:
-            assert torch.equal(a[k], b[k]), k
+    base = dict(dim=128, depth=2, heads=2, attn_dropout=0.0, ff_dropout=0.1)
+    variants = [dict(), dict(use_conv_ff=False, relative_position_bias_type="t5"),
+                dict(relative_position_bias_type="none", use_absolute_position_embeddings=True)]
+    for extra in variants:
+        kw = dict(base, **extra)
+        for mine, theirs in [(O.create_semantic_transformer, ref.create_semantic_transformer),
+                             (O.create_coarse_transformer, ref.create_coarse_transformer),
+                             (O.create_fine_transformer, ref.create_fine_transformer)]:
+            torch.manual_seed(0); a = mine(**kw).state_dict()
+            torch.manual_seed(0); b = theirs(**kw).state_dict()
+            assert list(a.keys()) == list(b.keys()), extra
+            for k in a:
+                assert torch.equal(a[k], b[k]), (extra, k)
 
 
 def test_no_cpu_fallback():
@@ -66,8 +70,8 @@ def test_no_cpu_fallback():
 
 
 def test_unsupported_configs_fail_loudly():
-    for kw in [dict(use_conv_ff=False), dict(relative_position_bias_type="t5"), dict(use_absolute_position_embeddings=True),
-               dict(non_causal_prefix_size=4), dict(attn_dropout=0.1), dict(use_memory_efficient_attention=True)]:
+    for kw in [dict(non_causal_prefix_size=4), dict(attn_dropout=0.1), dict(use_memory_efficient_attention=True),
+               dict(has_condition=True)]:
         with pytest.raises(NotImplementedError):
             O.create_semantic_transformer(dim=64, depth=1, heads=1, **kw)
 

@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from oracle import restatement as R
-from open_musiclm_b200.dist_utils import allreduce_sum_, grad_prescale, rank_seed
+from open_musiclm_b200.dist_utils import BucketReducer, allreduce_sum_, grad_prescale, plan_buckets, rank_seed
 
 
 def _cfg():
@@ -63,3 +63,68 @@ def test_rank_seeds_differ_and_single_process_is_identity():
     assert rank_seed(0, 0) != rank_seed(0, 1) and rank_seed(3, 2) == rank_seed(3, 2)
     x = torch.arange(5.0)
     assert torch.equal(allreduce_sum_(x.clone()), x) and grad_prescale() == 1.0
+
+
+def _toy_layout(depth=5):
+    """Arena layout with the engine's ordering: [embeddings | logit heads | layer matrices | rel-pos || 1-D params], 64-aligned."""
+    names = ["embeddings.0.weight", "embeddings.1.weight", "logit_weights.0", "logit_weights.1"]
+    for l in range(depth):
+        names += [f"transformer.layers.{l}.0.to_q.weight", f"transformer.layers.{l}.0.to_kv.weight", f"transformer.layers.{l}.0.to_out.0.weight",
+                  f"transformer.layers.{l}.2.1.weight", f"transformer.layers.{l}.2.2.ds_conv.weight", f"transformer.layers.{l}.2.6.weight"]
+    names += ["transformer.rel_pos_bias.net.0.0.weight", "transformer.rel_pos_bias.net.3.weight", "start_tokens.0", "start_tokens.1"]
+    for l in range(depth):
+        names += [f"transformer.layers.{l}.0.q_scale", f"transformer.layers.{l}.0.norm.gamma", f"transformer.layers.{l}.2.4.gamma"]
+    names += ["transformer.rel_pos_bias.net.0.0.bias", "transformer.norm.gamma"]
+    layout, sizes, off = {}, {}, 0
+    for i, n in enumerate(names):
+        sizes[n] = 37 + 101 * (i % 7)
+        layout[n] = off
+        off = (off + sizes[n] + 63) // 64 * 64
+    return layout, sizes, off
+
+
+def test_bucket_plan_tiles_the_arena_in_backward_order():
+    layout, sizes, total = _toy_layout(5)
+    plan = plan_buckets(layout, sizes, total, 5, min_elems=700)       # small buckets: layers get merged in pairs
+    trig = [t for t, _ in plan]
+    assert trig[0] == "heads" and trig[-1] == "tail" and trig[1:-1] == sorted(trig[1:-1], key=lambda t: -int(t[5:]))
+    assert trig[-2] == "layer0"
+    covered = sorted(s for _, sl in plan for s in sl)
+    assert covered[0][0] == 0 and covered[-1][1] == total and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+    # a layer's matrices are reduced no earlier than that layer's own trigger
+    for l in range(5):
+        first = layout[f"transformer.layers.{l}.0.to_q.weight"]
+        owner = next(t for t, sl in plan if any(lo <= first < hi for lo, hi in sl))
+        assert owner.startswith("layer") and int(owner[5:]) <= l
+    one = plan_buckets(layout, sizes, total, 5, min_elems=1 << 30)    # everything merged: heads, one layer bucket, tail
+    assert [t for t, _ in one] == ["heads", "layer0", "tail"]
+
+
+def _bucket_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    layout, sizes, total = _toy_layout(4)
+    plan = plan_buckets(layout, sizes, total, 4, min_elems=500)
+    g = torch.Generator().manual_seed(100 + rank)
+    flat = torch.randn(total, generator=g)
+    red = BucketReducer(flat, plan, None, side_stream=None)
+    red.begin()
+    red.fire("heads")
+    for l in reversed(range(4)):
+        red.fire(f"layer{l}")          # triggers of merged-away layers are ignored
+    red.fire("tail")
+    red.join()
+    if rank == 0:
+        torch.save(flat, out)
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_equals_one_allreduce(tmp_path):
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    out = str(tmp_path / "flat.pt")
+    mp.spawn(_bucket_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    _, _, total = _toy_layout(4)
+    ref = sum(torch.randn(total, generator=torch.Generator().manual_seed(100 + r)) for r in range(2))
+    assert torch.equal(got, ref)

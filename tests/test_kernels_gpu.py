@@ -73,6 +73,10 @@ def test_embed_gather_scatter(lib):
     lib.embed_gather(table, src, x)
     ref = torch.where((src >= 0)[:, None], table[src.clamp_min(0).long()], torch.zeros(1, device=DEV))
     assert torch.equal(x, ref)
+    src2 = torch.randint(-1, 500, (64,), device=DEV, dtype=torch.int32)      # second row (absolute position embeddings)
+    lib.embed_gather(table, src, x, src2)
+    ref2 = ref + torch.where((src2 >= 0)[:, None], table[src2.clamp_min(0).long()], torch.zeros(1, device=DEV))
+    assert torch.equal(x, ref2)
     dx = torch.randn(64, 256, device=DEV)
     dt = torch.zeros_like(table)
     lib.embed_scatter_add(dt, src, dx, 0.1)

@@ -16,7 +16,9 @@ GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "tiny_
 def cfg_from_fixture(fx):
     kw = fx["kwargs"]
     common = dict(dim=kw["dim"], depth=kw["depth"], heads=kw["heads"], ff_dropout=kw["ff_dropout"],
-                  grad_shrink_alpha=kw["grad_shrink_alpha"], ce_weights=fx["ce_weights"])
+                  grad_shrink_alpha=kw["grad_shrink_alpha"], ce_weights=fx["ce_weights"],
+                  use_conv_ff=kw.get("use_conv_ff", True), rel_pos_bias_type=kw.get("relative_position_bias_type", "continuous"),
+                  abs_pos=kw.get("use_absolute_position_embeddings", False))
     cb = kw.get("clap_codebook_size", 1024)
     if fx["stage"] == "semantic":
         return R.semantic_cfg(codebook=cb, n_clap_q=kw["num_clap_quantizers"], **common)
@@ -133,3 +135,31 @@ def test_restatement_matches_reference_live(stage):
     assert abs(float(loss) - float(loss_ref)) / float(loss_ref) < 1e-5
     for a, b in zip(logits, logits_ref):
         assert rel(a, b.permute(0, 2, 1)) < 2e-5
+
+
+GEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "gen_*.pt")))
+
+
+def _cfg_of(fx):
+    kw = fx["kwargs"]
+    base = dict(dim=kw["dim"], depth=kw["depth"], heads=kw["heads"], codebook=kw.get("clap_codebook_size", 1024),
+                n_clap_q=kw.get("num_clap_quantizers", 12))
+    if fx["stage"] == "semantic":
+        return R.semantic_cfg(**base)
+    if fx["stage"] == "coarse":
+        return R.coarse_cfg(n_coarse_q=kw["num_coarse_quantizers"], **base)
+    return R.fine_cfg(n_coarse_q=kw["num_coarse_quantizers"], n_fine_q=kw["num_fine_quantizers"], **base)
+
+
+@pytest.mark.parametrize("path", GEN, ids=[os.path.basename(p) for p in GEN])
+def test_generate_restatement_reproduces_reference_tokens(path):
+    """oracle.generate against the token sequences the REAL reference's wrapper.generate produced under the same
+    Gumbel noise stream (oracle/make_golden_generate.py): bit-exact, including the eos handling and the [b, n, q] fold."""
+    fx = torch.load(path, weights_only=False)
+    cfg = _cfg_of(fx)
+    uni = fx["uniforms"]
+    out = R.generate(cfg, fx["state_dict"], [t.numpy() for t in fx["cond"]], lambda step, shape: uni[step],
+                     pred_token_ids=None if fx["prefix"] is None else fx["prefix"].numpy(), max_time_steps=fx["max_time_steps"],
+                     filter_thres=fx["filter_thres"], temperature=fx["temperature"],
+                     include_eos_in_output=fx["include_eos_in_output"], allow_eos_in_output=fx["allow_eos_in_output"])
+    assert out.shape == fx["out"].shape and torch.equal(out, fx["out"])

@@ -99,7 +99,7 @@ def gpu(case, ref, mode):
         rows = []
         for k in ref["names"]:
             g_ref = ref["grads"][k]
-            if float(g_ref.norm()) < 1e-9:
+            if float(g_ref.norm()) < 1e-9 or k.endswith("rel_pos_bias.net.3.bias"):     # analytically zero gradient
                 continue
             mine = tr.eng.gview[k]
             rows.append((k, cos(mine, g_ref), rel(mine, g_ref), g_ref.numel()))
@@ -108,6 +108,9 @@ def gpu(case, ref, mode):
         res["grad_over_2e-2"] = [(k, round(c, 5), round(r, 5)) for k, c, r, n in rows if r > 2e-2 or c < 0.999]
         res["grad_median_rel"] = sorted(r for _, _, r, _ in rows)[len(rows) // 2]
         res["grad_relpos"] = [(k, round(c, 6), round(r, 5)) for k, c, r, n in rows if "rel_pos_bias" in k]
+        kb, kw = "transformer.rel_pos_bias.net.3.bias", "transformer.rel_pos_bias.net.3.weight"
+        res["net3_bias_norms"] = dict(mine=float(tr.eng.gview[kb].double().norm()), ref=float(ref["grads"][kb].double().norm()),
+                                      ref_net3_weight=float(ref["grads"][kw].double().norm()))
         tr.eng.arena_g.zero_()
     del tr, m
     torch.cuda.empty_cache()

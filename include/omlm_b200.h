@@ -186,6 +186,11 @@ int omlm_pack(const float* src, long src_ld, int rows_valid, int cols_valid, voi
 int omlm_unpack_add(const float* packed, long p_ld, int rows_p, int cols_p, float* dst, long dst_ld, int rows_valid,
                     int cols_valid, int split_dst, int split_src, void* stream);
 
+/* ---- token store (open_musiclm/data.py:304-438: PreprocessedDataset crops) -----------------------------------------
+ * out[b, t, c] = src[(start[b] + t) * width + c] (uint16 token ids widened to int64): one crop per batch row out of a
+ * device-resident flat token array; `start` are rows (time steps), not elements. */
+int omlm_gather_windows(const void* src_i16, const long long* start, long long* out, int len, int width, int B, void* stream);
+
 /* ---- incremental (KV-cache) decoding: TokenConditionedTransformerWrapper.generate (open_musiclm.py:253-326) ----------
  * One new position per sequence and step instead of the reference's full-prefix forward per sampled token
  * (open_musiclm.py:303-307).  B <= 16 rows; SIMT weight-streaming kernels (csrc/decode.cu).

@@ -211,3 +211,31 @@ int omlm_embed_scatter_add(float* dtable, const int* src_row, const float* dx, i
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ token store
+// Batch assembly from a device-resident token store (the pre-tokenised dataset of open_musiclm/data.py:304-438 kept in
+// HBM as flat int16 arrays): out[b, t, c] = (long) src[(start[b] + t) * width + c] for t < len, c < width.  One random
+// crop per batch row; the crop indices are drawn on the host with the reference's arithmetic, the copy never leaves HBM.
+namespace omlm {
+__global__ void gather_windows_kernel(const short* __restrict__ src, const long long* __restrict__ start, long long* __restrict__ out,
+                                      int len, int width, int B) {
+  const long long per_row = static_cast<long long>(len) * width;
+  const long long total = per_row * B;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / per_row);
+    const long long r = i - b * per_row;
+    out[i] = static_cast<unsigned short>(src[start[b] * width + r]);
+  }
+}
+}  // namespace omlm
+
+extern "C" int omlm_gather_windows(const void* src_i16, const long long* start, long long* out, int len, int width, int B, void* stream) {
+  using namespace omlm;
+  OMLM_CHECK_ARG(B > 0 && len >= 0 && width > 0, "gather_windows: bad shape");
+  if (len == 0) return 0;
+  const long long total = static_cast<long long>(len) * width * B;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(num_sms()) * 8));
+  gather_windows_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const short*>(src_i16), start, out, len, width, B);
+  OMLM_LAUNCH_CHECK();
+  return 0;
+}

@@ -332,3 +332,11 @@ def decode_conv_geglu(u_new, state, conv_w, h_out, rowsum):
 def sample(logits, C, top_k, temperature, allow_eos, uniform, seed, tokens, next_row, row_offset, counters, pos, B):
     call("omlm_sample", _p(logits), _L(logits.stride(0)), _I(C), _I(top_k), _F(temperature), _I(int(allow_eos)), _p(uniform),
          _p(seed), _p(tokens), _L(tokens.stride(0)), _p(next_row), _I(row_offset), _p(counters), _p(pos), _I(B), _stream())
+
+
+def gather_windows(src_i16, start, out):
+    """out[b, t, c] = src[(start[b] + t), c] for a flat [T_total, width] int16 token store (ids are uint16)."""
+    B, length = out.shape[0], out.shape[1]
+    width = src_i16.shape[1] if src_i16.dim() == 2 else 1
+    assert src_i16.dtype == torch.int16 and start.dtype == torch.int64 and out.dtype == torch.int64 and out.is_contiguous()
+    call("omlm_gather_windows", _p(src_i16), _p(start), _p(out), _I(length), _I(width), _I(B), _stream())

@@ -280,6 +280,72 @@ class HotPathTrainer:
     def grad_norm(self):
         return torch.sqrt(self.eng.sumsq).float()
 
+    # ------------------------------------------------------------------------------------------- checkpoint FILES
+    def _torch_optimizer(self):
+        """A torch.optim.AdamW over the module's parameters, grouped like the reference's get_optimizer
+        (optimizer.py:3-34: ndim >= 2 with weight decay, the rest without) and carrying THIS trainer's moments, step
+        count and current learning rate — used only to read / write the reference's optimizer checkpoint format."""
+        params = list(self.transformer.parameters())
+        wd_params = [p for p in params if p.ndim >= 2]
+        no_wd = [p for p in params if p.ndim < 2]
+        opt = torch.optim.AdamW([{"params": wd_params}, {"params": no_wd, "weight_decay": 0}], lr=self.lr, weight_decay=self.wd,
+                                betas=tuple(self.betas), eps=self.eps)
+        return opt, wd_params + no_wd
+
+    def _lr_factor(self, steps):
+        return 1.0 if self.lr_warmup <= 0 else 1e-7 + (1.0 - 1e-7) * min(steps, self.lr_warmup) / self.lr_warmup
+
+    def save(self, model_path, optim_path, scheduler_path=None):
+        """SingleStageTrainer.save (trainer.py:359-372): transformer state_dict, torch AdamW state_dict, LinearLR state_dict —
+        files the reference's trainer (and scripts/train_utils.py) can load back."""
+        eng = self.eng
+        torch.save({k: v.detach().clone() for k, v in self.transformer.state_dict().items()}, model_path)
+        opt, ordered = self._torch_optimizer()
+        name_of = {id(p): n for n, p in self.transformer.named_parameters()}
+        if self.steps > 0:
+            for p in ordered:
+                o = eng.layout[name_of[id(p)]]
+                opt.state[p] = {"step": torch.tensor(float(self.steps)), "exp_avg": eng.adam_m[o:o + p.numel()].view(p.shape).clone(),
+                                "exp_avg_sq": eng.adam_v[o:o + p.numel()].view(p.shape).clone()}
+        sched = None
+        if self.lr_warmup > 0:
+            sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1e-7, end_factor=1.0, total_iters=self.lr_warmup)
+            lr_now = self.lr * self._lr_factor(self.steps)
+            sched.last_epoch, sched._step_count = self.steps, self.steps + 1
+            sched._last_lr = [lr_now for _ in opt.param_groups]
+            for g in opt.param_groups:
+                g["lr"] = lr_now
+        torch.save(opt.state_dict(), optim_path)
+        if sched is not None:
+            assert scheduler_path is not None, "lr_warmup is used: a scheduler checkpoint path is needed"
+            torch.save(sched.state_dict(), scheduler_path)
+
+    def load(self, model_path, optim_path, scheduler_path=None, steps=0):
+        """SingleStageTrainer.load (trainer.py:374-391): accepts the reference's own checkpoint files."""
+        eng = self.eng
+        self.transformer.load_state_dict(torch.load(model_path, map_location=eng.dev))
+        opt, ordered = self._torch_optimizer()
+        opt.load_state_dict(torch.load(optim_path, map_location=eng.dev))
+        name_of = {id(p): n for n, p in self.transformer.named_parameters()}
+        eng.adam_m.zero_(); eng.adam_v.zero_()
+        opt_steps = 0
+        for p in ordered:
+            st = opt.state.get(p)
+            if st:
+                o = eng.layout[name_of[id(p)]]
+                eng.adam_m[o:o + p.numel()].view(p.shape).copy_(st["exp_avg"])
+                eng.adam_v[o:o + p.numel()].view(p.shape).copy_(st["exp_avg_sq"])
+                opt_steps = max(opt_steps, int(float(st["step"])))
+        self.steps = opt_steps
+        if scheduler_path is not None and self.lr_warmup > 0:
+            sd = torch.load(scheduler_path, map_location="cpu")
+            self.steps = int(sd["last_epoch"])
+        elif self.lr_warmup > 0:
+            raise AssertionError("the config specifies lr warmup is used, but no scheduler checkpoint is given. try setting lr_warmup to 0.")
+        eng.arena_g.zero_()
+        eng.refresh_packed(force=True)
+        return self.steps
+
     # ------------------------------------------------------------------------------------------- checkpointing
     def state_dict(self):
         """Optimiser / scheduler / RNG state needed to resume training exactly where it stopped (the reference's

@@ -385,6 +385,40 @@ def measure(key, args, world, rank, local, inst, full):
     return res
 
 
+def measure_generation(seconds=10, batch=1):
+    """BASELINE.json configs[4]: semantic -> coarse -> fine generation of `seconds` of audio through the reference's
+    sliding windows (open_musiclm.py:925-1031) on the KV-cache decode path, random-init musiclm_small stages, synthetic
+    clap ids.  tokens/s = sampled tokens of the three streams / device time (CUDA events) of the SECOND run (the first
+    one captures the per-quantizer CUDA graphs)."""
+    import torch
+    import open_musiclm_b200 as O
+    torch.manual_seed(0)
+    mk = dict(**COMMON, depth=6, heads=8)
+    sem = O.create_semantic_transformer(**mk).cuda().eval()
+    coa = O.create_coarse_transformer(**mk, num_coarse_quantizers=3).cuda().eval()
+    fin = O.create_fine_transformer(**mk, num_coarse_quantizers=3, num_fine_quantizers=5).cuda().eval()
+    mlm = O.MusicLM(semantic_transformer=sem, coarse_transformer=coa, fine_transformer=fin)
+    g = torch.Generator().manual_seed(1234)
+    clap = torch.randint(0, 1024, (batch, 12), generator=g).cuda()
+    times = []
+    for it in range(2):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        ac, s, c, f = mlm.generate_tokens(clap_token_ids=clap, output_seconds=seconds, return_all=True)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append((e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))
+    n_tok = batch * (s.shape[1] * s.shape[2] + c.shape[1] * c.shape[2] + f.shape[1] * f.shape[2])
+    ms_dev, ms_wall = times[-1]
+    return {"workload": f"configs[4]: musiclm_small semantic->coarse->fine generation of {seconds} s of audio, batch {batch}, KV-cache decode, "
+                        "sliding windows of MusicLM.forward, random-init weights, synthetic clap ids",
+            "tokens_in_output": n_tok, "streams": {"semantic": list(s.shape), "coarse": list(c.shape), "fine": list(f.shape)},
+            "ms_device": ms_dev, "ms_wall": ms_wall, "ms_first_run_incl_graph_capture": times[0][1],
+            "tokens_per_s": n_tok / (ms_wall * 1e-3), "audio_seconds_per_second": seconds / (ms_wall * 1e-3)}
+
+
 def summary(res):
     """Sub-result for a BASELINE config reported beside the headline."""
     fl, pk = res["fl"], res["peaks"]
@@ -418,6 +452,12 @@ def run_b200(args):
         r = measure(key, args, world, rank, local, inst, full=False)
         r.pop("tr")
         extras[key] = summary(r)
+        torch.cuda.empty_cache()
+    if "cfg5" in [k for k in args.extra.split(",")] or args.extra == "cfg3,cfg4":
+        try:
+            extras["cfg5"] = measure_generation()
+        except Exception as e:            # the headline must still be printed
+            extras["cfg5"] = {"error": f"{type(e).__name__}: {e}"}
         torch.cuda.empty_cache()
     gemm_traffic = {}
     try:   # DRAM bytes of the GEMM family from the committed ncu --set full capture (tools/ncu_summarize.py)

@@ -111,6 +111,7 @@ def test_generate_matches_reference_tokens_under_fixed_noise(path):
         for s in range(mine.shape[1]):
             if ref[b, s] == -1:           # after an eos both are masked
                 assert mine[b, s] == -1
+                exact += 1
                 continue
             if mine[b, s] != ref[b, s]:
                 gap = float(otrace[s][1][b])

@@ -128,8 +128,9 @@ int omlm_attn_bwd(const void* qn, const void* kvn, const void* d_o, const void* 
                   float* dqn, float* dkvn, float* dtable, int B, int N, int heads, float scale,
                   void* stream);
 
-/* tcgen05/TMEM/TMA backward (same contract; the bias gradient -- diagonal sums of dS -- is formed inside the kernel from
- * an fp32-class hi/lo split of dS, no scratch tensor). */
+/* tcgen05/TMEM/TMA backward: dqn and dkvn are OVERWRITTEN (its first kernel clears them, the main kernel reduces into
+ * them), dtable is accumulated (+=: one table gradient over all layers).  The bias gradient -- diagonal sums of dS -- is
+ * formed inside the kernel from an fp32-class hi/lo split of dS, no scratch tensor. */
 int omlm_attn_bwd_tc(const void* qn, const void* kvn, const void* d_o, const void* o, const float* lse2,
                      const float* table, int table_ld, const unsigned char* key_mask, float* dsum_scratch,
                      float* dqn, float* dkvn, float* dtable, int B, int N, int heads,
@@ -153,7 +154,8 @@ int omlm_ffn_norm_fwd(const void* h, const float* rowsum, const float* gamma, vo
                       void* keep_bits, long M, int F, int Fp, float drop_p, const unsigned long long* seed, int layer,
                       int act_f16, void* stream);
 /* dhn, hn (saved forward output), keep_bits (from omlm_ffn_norm_fwd; may be NULL when drop_p == 0) ->
- * du bf16 [B*N, 2Fp]; dgamma [Fp] += ; dconv_w [2Fp,3] += ; rowstat_scratch fp32 [B*N, 2]. */
+ * du bf16 [B*N, 2Fp]; dgamma [Fp] and dconv_w [2Fp,3] are OVERWRITTEN (cleared by the statistics kernel, reduced into
+ * by the tile kernel); rowstat_scratch fp32 [B*N, 2]. */
 int omlm_ffn_mid_bwd(const void* dhn, const void* hn, const void* u, const float* stats, const float* conv_w,
                      const float* gamma, const void* keep_bits, float* rowstat_scratch, void* du, float* dgamma,
                      float* dconv_w, int B, int N, int F, int Fp, float drop_p, int act_f16, void* stream);

@@ -44,6 +44,7 @@ __device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
 __global__ void __launch_bounds__(256)
 attn_bwd_dsum_kernel(const __nv_bfloat16* __restrict__ d_o, const __nv_bfloat16* __restrict__ o,
                      float* __restrict__ dsum, long rows) {
+  pdl_prologue();
   const long r = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
   const int sub = threadIdx.x & 7;
   float s = 0.f;
@@ -70,6 +71,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qn, const __nv_bfloat16* __res
                 const unsigned char* __restrict__ key_mask, float* __restrict__ dqn,
                 float* __restrict__ dkvn, float* __restrict__ dtable, int N, int h, float scale,
                 int tiles_per_chunk, int units_per_batch) {
+  pdl_prologue();
   extern __shared__ __align__(128) uint8_t smem_raw[];
   AttnBwdSmem& sm = *reinterpret_cast<AttnBwdSmem*>(smem_raw);
   const int R = N * h;
@@ -341,7 +343,7 @@ extern "C" int omlm_attn_bwd(const void* qn, const void* kvn, const void* d_o, c
   OMLM_CHECK_ARG(table_ld >= N, "attn_bwd: bias table shorter than the sequence");
   auto st = reinterpret_cast<cudaStream_t>(stream);
   const long rows = static_cast<long>(B) * N * heads;
-  attn_bwd_dsum_kernel<<<static_cast<int>((rows * 8 + 255) / 256), 256, 0, st>>>(
+  OMLM_KLAUNCH((attn_bwd_dsum_kernel), static_cast<int>((rows * 8 + 255) / 256), 256, 0, st, 
       reinterpret_cast<const __nv_bfloat16*>(d_o), reinterpret_cast<const __nv_bfloat16*>(o), dsum_scratch, rows);
   OMLM_LAUNCH_CHECK();
   static bool configured = false;
@@ -368,7 +370,7 @@ extern "C" int omlm_attn_bwd(const void* qn, const void* kvn, const void* d_o, c
     const int first = (kt * kBKV * heads) / kBQ;
     units_per_batch += (n_row_tiles - first + tiles_per_chunk - 1) / tiles_per_chunk;
   }
-  attn_bwd_kernel<<<B * units_per_batch, kBwdThreads, smem, st>>>(
+  OMLM_KLAUNCH((attn_bwd_kernel), B * units_per_batch, kBwdThreads, smem, st, 
       reinterpret_cast<const __nv_bfloat16*>(qn), reinterpret_cast<const __nv_bfloat16*>(kvn),
       reinterpret_cast<const __nv_bfloat16*>(d_o), lse2, dsum_scratch, table, table_ld, key_mask, dqn, dkvn, dtable,
       N, heads, scale, tiles_per_chunk, units_per_batch);

@@ -123,6 +123,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    int table_ld, const unsigned char* __restrict__ key_mask, float* __restrict__ dqn,
                    float* __restrict__ dkvn, float* __restrict__ dtable, int N, int h, float scale, int W, int Wd,
                    int Wacc, int tiles_per_chunk, int units_per_batch) {
+  pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBoBar);
@@ -176,6 +177,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // private set-up done: from here on global memory written by the previous kernel is touched
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -427,14 +429,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
-// D[r] = sum_d dO[r, d] * O[r, d]
+// D[r] = sum_d dO[r, d] * O[r, d];  also clears the dQ / dK|dV accumulators the main kernel reduces into
+// (dqn [rows, 64] fp32: this thread's 8 columns; dkvn: kv_vec4 float4s spread over the grid)
 __global__ void __launch_bounds__(256)
 attn_bwd_tc_dsum_kernel(const __nv_bfloat16* __restrict__ d_o, const __nv_bfloat16* __restrict__ o,
-                        float* __restrict__ dsum, long rows) {
-  const long r = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
+                        float* __restrict__ dsum, long rows, float* __restrict__ dqn, float* __restrict__ dkvn, long kv_vec4) {
+  pdl_prologue();
+  const long tid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long r = tid >> 3;
   const int sub = threadIdx.x & 7;
   float s = 0.f;
+  for (long i = tid; i < kv_vec4; i += static_cast<long>(gridDim.x) * blockDim.x)     // (fewer threads than float4s when heads < 4)
+    reinterpret_cast<float4*>(dkvn)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (r < rows) {
+    float4* zq = reinterpret_cast<float4*>(dqn + r * 64 + sub * 8);
+    zq[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    zq[1] = make_float4(0.f, 0.f, 0.f, 0.f);
     const uint4 a = *reinterpret_cast<const uint4*>(d_o + r * 64 + sub * 8);
     const uint4 bq = *reinterpret_cast<const uint4*>(o + r * 64 + sub * 8);
     const uint32_t aa[4] = {a.x, a.y, a.z, a.w}, bb[4] = {bq.x, bq.y, bq.z, bq.w};
@@ -462,8 +472,9 @@ extern "C" int omlm_attn_bwd_tc(const void* qn, const void* kvn, const void* d_o
   auto st = reinterpret_cast<cudaStream_t>(stream);
   const long R = static_cast<long>(N) * heads;
   const long rows = static_cast<long>(B) * R;
-  attn_bwd_tc_dsum_kernel<<<static_cast<int>((rows * 8 + 255) / 256), 256, 0, st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(d_o), reinterpret_cast<const __nv_bfloat16*>(o), dsum_scratch, rows);
+  OMLM_KLAUNCH((attn_bwd_tc_dsum_kernel), static_cast<int>((rows * 8 + 255) / 256), 256, 0, st, 
+      reinterpret_cast<const __nv_bfloat16*>(d_o), reinterpret_cast<const __nv_bfloat16*>(o), dsum_scratch, rows,
+      dqn, dkvn, static_cast<long>(B) * N * 128 / 4);
   OMLM_LAUNCH_CHECK();
   const int Wd = (kBtBQ + heads - 1) / heads + 1 + (kBtBK - 1);
   int W = Wd;
@@ -506,7 +517,7 @@ extern "C" int omlm_attn_bwd_tc(const void* qn, const void* kvn, const void* d_o
     configured = smem_bytes;
   }
   const int units_per_batch = static_cast<int>(units_of(tiles_per_chunk));
-  attn_bwd_tc_kernel<<<B * units_per_batch, kBtThreads, smem_bytes, st>>>(
+  OMLM_KLAUNCH((attn_bwd_tc_kernel), B * units_per_batch, kBtThreads, smem_bytes, st, 
       tmQ, tmDO, tmKV, lse2, dsum_scratch, table, table_ld, key_mask, dqn, dkvn, dtable, N, heads, scale, W, Wd, Wacc,
       tiles_per_chunk, units_per_batch);
   OMLM_LAUNCH_CHECK();

@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qn, const __nv_bfloat16* __restrict__ kvn,
                 const float* __restrict__ table, int table_ld, const unsigned char* __restrict__ key_mask,
                 __nv_bfloat16* __restrict__ out, float* __restrict__ lse2, int N, int h, float scale) {
+  pdl_prologue();
   extern __shared__ __align__(128) uint8_t smem_raw[];
   AttnFwdSmem& sm = *reinterpret_cast<AttnFwdSmem*>(smem_raw);
   const int b = blockIdx.y;
@@ -215,7 +216,7 @@ extern "C" int omlm_attn_fwd(const void* qn, const void* kvn, const float* table
   }
   const int R = N * heads;
   dim3 grid((R + kAttnBR - 1) / kAttnBR, B);
-  attn_fwd_kernel<<<grid, kAttnThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+  OMLM_KLAUNCH((attn_fwd_kernel), grid, kAttnThreads, smem, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(qn), reinterpret_cast<const __nv_bfloat16*>(kvn), table, table_ld,
       key_mask, reinterpret_cast<__nv_bfloat16*>(out), lse2, N, heads, scale);
   OMLM_LAUNCH_CHECK();

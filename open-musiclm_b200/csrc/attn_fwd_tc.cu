@@ -60,6 +60,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    const float* __restrict__ table, int table_ld, const unsigned char* __restrict__ key_mask,
                    __nv_bfloat16* __restrict__ out, float* __restrict__ lse2, int N, int h, float scale, int W,
                    int Wd, int nbatch) {
+  pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // pointer arithmetic (not an integer round trip) keeps the shared address space visible to the compiler: LDS/STS, not generic LD/ST
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -104,6 +105,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // private set-up done: from here on global memory written by the previous kernel is touched
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
@@ -368,7 +370,7 @@ extern "C" int omlm_attn_fwd_tc(const void* qn, const void* kvn, const float* ta
   }
   dim3 grid(static_cast<unsigned>((R + 2 * kTcBQ - 1) / (2 * kTcBQ)) * B, B);   // x: (row block, batch) in LPT order; y only carries B
   grid.y = 1;
-  attn_fwd_tc_kernel<<<grid, kTcThreads, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(
+  OMLM_KLAUNCH((attn_fwd_tc_kernel), grid, kTcThreads, smem_bytes, reinterpret_cast<cudaStream_t>(stream), 
       tmQ, tmKV, table, table_ld, key_mask, reinterpret_cast<__nv_bfloat16*>(out), lse2, N, heads, scale, W, Wd, B);
   OMLM_LAUNCH_CHECK();
   return 0;

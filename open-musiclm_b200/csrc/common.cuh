@@ -34,11 +34,51 @@ void set_last_error(const char* fmt, ...);
 int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t dim0, uint64_t dim1,
                       uint64_t pitch_bytes, uint32_t box0, uint32_t box1);
 
+// 2-D tensor map of 2-byte (elem_bytes = 2) or fp32 (elem_bytes = 4) elements, SWIZZLE_128B, box0 * elem_bytes = 128:
+// the staging layout of the GEMM epilogue's TMA stores / residual loads (32-row boxes).
+int make_tmap_2d(CUtensorMap* out, int elem_bytes, const void* gptr, uint64_t dim0, uint64_t dim1, uint64_t pitch_bytes,
+                 uint32_t box0, uint32_t box1);
+
 // 3-D bf16 tensor map (dim0 contiguous), SWIZZLE_128B, box {box0, box1, 1}: out-of-range rows/planes are clipped.
 int make_tmap_bf16_3d(CUtensorMap* out, const void* gptr, uint64_t dim0, uint64_t dim1, uint64_t dim2,
                       uint64_t pitch1_bytes, uint64_t pitch2_bytes, uint32_t box0, uint32_t box1);
 
 int num_sms();
+
+// ---- kernel launches: programmatic dependent launch (PDL), OFF by default ---------------------------------------------
+// Every kernel of the library can be launched with the programmatic-stream-serialization attribute (OMLM_PDL=1); it then
+//   * executes griddepcontrol.launch_dependents first thing (the next kernel's CTAs may become resident as soon as
+//     this grid's CTAs have all started and resources free up), and
+//   * executes griddepcontrol.wait before its first global-memory access (it blocks until the previous grid has
+//     completed and its writes are visible), after whatever private set-up it can do early.
+// Measured on the cfg2 training step (CUDA-graph replay, same box, A/B): 11.52 ms with PDL against 11.35 ms without --
+// the persistent GEMM CTAs own the whole shared memory of their SM, so a dependent CTA cannot become resident before
+// its predecessor exits, and the programmatic graph edges cost more than the launch gaps they hide.  Hence the default
+// is the plain stream order; without the attribute both instructions are no-ops.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() { pdl_launch_dependents(); pdl_wait(); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#define OMLM_KLAUNCH(kern, grid, block, smem, stream, ...)                                                   \
+  do {                                                                                                       \
+    cudaError_t _le = ::omlm::launch_k(kern, dim3(grid), dim3(block), smem, stream, __VA_ARGS__);            \
+    if (_le != cudaSuccess) {                                                                                \
+      ::omlm::set_last_error("%s:%d launch of %s -> %s", __FILE__, __LINE__, #kern, cudaGetErrorString(_le)); \
+      return 1000 + static_cast<int>(_le);                                                                   \
+    }                                                                                                        \
+  } while (0)
 
 // ---- device math --------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

@@ -43,6 +43,7 @@ constexpr int kSkWarps = 8, kSkRowsPerWarp = 2;
 
 __global__ void __launch_bounds__(kSkWarps * 32)
 skinny_gemm_kernel(const SkinnyArgs a) {
+  pdl_prologue();
   extern __shared__ __align__(16) uint8_t sk_smem[];
   uint16_t* sA = reinterpret_cast<uint16_t*>(sk_smem);              // [B][K] in the operand format
   __shared__ float s_mean[kDecMaxB], s_rstd[kDecMaxB];
@@ -152,6 +153,7 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q_raw, const __nv_bfloat16*
                    const float* __restrict__ q_scale, const float* __restrict__ k_scale,
                    __nv_bfloat16* __restrict__ cache, long cache_ld_b, const float* __restrict__ table, int table_ld,
                    const int* __restrict__ pos_ptr, __nv_bfloat16* __restrict__ out, int h, float scale) {
+  pdl_prologue();
   extern __shared__ __align__(16) float ad_smem[];
   float* sc = ad_smem;                       // [n + 1] scores, then probabilities
   __shared__ float sq[64], sk[64], sv[64];
@@ -257,6 +259,7 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q_raw, const __nv_bfloat16*
 __global__ void __launch_bounds__(128)
 decode_conv_geglu_kernel(const uint16_t* __restrict__ u_new, uint16_t* __restrict__ state, const float* __restrict__ conv_w,
                          uint16_t* __restrict__ h_out, float* __restrict__ rowsum, int Fp, int f16) {
+  pdl_prologue();
   const int grp = blockIdx.x, b = blockIdx.y, c = threadIdx.x;
   const long col_v = static_cast<long>(grp) * 256 + c, col_g = col_v + 128;
   const long ld = 2L * Fp;
@@ -300,6 +303,7 @@ sample_kernel(const float* __restrict__ logits, long ld, int C, int k, float tem
               const float* __restrict__ uniform, const unsigned long long* __restrict__ seed_ptr,
               long long* __restrict__ tokens, long tokens_ld, int* __restrict__ next_row, int row_offset,
               int* __restrict__ step_ptr, int* __restrict__ pos_ptr, int B) {
+  pdl_prologue();
   extern __shared__ float sm_l[];          // [C] logits, then [C] sort keys
   float* lg = sm_l;
   uint32_t* key = reinterpret_cast<uint32_t*>(sm_l + C);
@@ -418,7 +422,7 @@ int omlm_skinny_gemm(const void* A, long lda, int prologue, const void* W, long 
     configured = smem;
   }
   const int rows_per_cta = kSkWarps * kSkRowsPerWarp;
-  skinny_gemm_kernel<<<(N + rows_per_cta - 1) / rows_per_cta, kSkWarps * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  OMLM_KLAUNCH((skinny_gemm_kernel), (N + rows_per_cta - 1) / rows_per_cta, kSkWarps * 32, smem, reinterpret_cast<cudaStream_t>(stream), a);
   OMLM_LAUNCH_CHECK();
   return 0;
 }
@@ -435,7 +439,7 @@ int omlm_attn_decode(const void* q_raw, const void* kv_raw, const float* q_scale
     OMLM_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  attn_decode_kernel<<<dim3(B, heads), kAdThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+  OMLM_KLAUNCH((attn_decode_kernel), dim3(B, heads), kAdThreads, smem, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(q_raw), reinterpret_cast<const __nv_bfloat16*>(kv_raw), q_scale, k_scale,
       reinterpret_cast<__nv_bfloat16*>(cache), cache_ld_b, table, table_ld, pos_ptr, reinterpret_cast<__nv_bfloat16*>(out), heads, scale);
   OMLM_LAUNCH_CHECK();
@@ -446,7 +450,7 @@ int omlm_decode_conv_geglu(const void* u_new, void* state, const float* conv_w, 
                            int act_f16, void* stream) {
   using namespace omlm;
   OMLM_CHECK_ARG(B >= 1 && Fp > 0 && Fp % 128 == 0, "decode_conv_geglu: bad shape");
-  decode_conv_geglu_kernel<<<dim3(Fp / 128, B), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  OMLM_KLAUNCH((decode_conv_geglu_kernel), dim3(Fp / 128, B), 128, 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const uint16_t*>(u_new), reinterpret_cast<uint16_t*>(state), conv_w, reinterpret_cast<uint16_t*>(h_out), rowsum, Fp, act_f16);
   OMLM_LAUNCH_CHECK();
   return 0;
@@ -457,7 +461,7 @@ int omlm_sample(const float* logits, long ld, int C, int top_k, float temperatur
                 int* pos_ptr, int B, void* stream) {
   using namespace omlm;
   OMLM_CHECK_ARG(B >= 1 && C >= 2 && C <= 16384 && temperature > 0.f && top_k >= 1 && top_k <= C, "sample: bad arguments");
-  sample_kernel<<<B, 256, 2 * C * 4, reinterpret_cast<cudaStream_t>(stream)>>>(logits, ld, C, top_k, temperature, allow_eos, uniform, seed, tokens,
+  OMLM_KLAUNCH((sample_kernel), B, 256, 2 * C * 4, reinterpret_cast<cudaStream_t>(stream), logits, ld, C, top_k, temperature, allow_eos, uniform, seed, tokens,
                                                                             tokens_ld, next_row, row_offset, step_ptr, pos_ptr, B);
   OMLM_LAUNCH_CHECK();
   return 0;

@@ -73,6 +73,7 @@ ffn_norm_fwd_kernel(const __nv_bfloat16* __restrict__ h, const float2* __restric
                     const float* __restrict__ gamma, __nv_bfloat16* __restrict__ hn, __nv_bfloat16* __restrict__ hn_copy, float2* __restrict__ stats,
                     uint8_t* __restrict__ keep_bits, long M, int F, int Fp, float drop_p,
                     const unsigned long long* __restrict__ seed_ptr, uint32_t layer) {
+  pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long row = static_cast<long>(blockIdx.x) * 8 + warp;
   if (row >= M) return;
@@ -127,8 +128,14 @@ ffn_norm_fwd_kernel(const __nv_bfloat16* __restrict__ h, const float2* __restric
 __global__ void __launch_bounds__(256)
 ffn_mid_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dhn, const __nv_bfloat16* __restrict__ hn,
                          const float* __restrict__ gamma, float2* __restrict__ rowstat, long M, int F, int Fp,
-                         float drop_p, const uint8_t* __restrict__ keep_bits) {
+                         float drop_p, const uint8_t* __restrict__ keep_bits, float* __restrict__ dgamma,
+                         float* __restrict__ dconv_w) {
+  pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the walk kernel reduces its parameter gradients into dgamma [Fp] and dconv_w [2 Fp, 3]: cleared here
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < 7L * Fp; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    if (i < Fp) dgamma[i] = 0.f; else dconv_w[i - Fp] = 0.f;
+  }
   const long row = static_cast<long>(blockIdx.x) * 8 + warp;
   if (row >= M) return;
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
@@ -182,6 +189,7 @@ __global__ void __launch_bounds__(kTileThreads, 2)
 ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, const float2* __restrict__ stats,
                         const float2* __restrict__ rowstat, __nv_bfloat16* __restrict__ du,
                         float* __restrict__ dgamma, float* __restrict__ dconv_w) {
+  pdl_prologue();
   extern __shared__ __align__(16) uint8_t tsm[];
   uint8_t* su = tsm + kTOffU;
   uint8_t* sd = tsm + kTOffD;
@@ -357,7 +365,7 @@ int omlm_ffn_norm_fwd(const void* h, const float* rowsum, const float* gamma, vo
   OMLM_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || (seed != nullptr && keep_bits != nullptr)),
                  "ffn_norm_fwd: dropout needs a seed and a keep_bits buffer");
   auto kern = act_f16 ? ffn_norm_fwd_kernel<true> : ffn_norm_fwd_kernel<false>;
-  kern<<<static_cast<int>((M + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  OMLM_KLAUNCH((kern), static_cast<int>((M + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(h), reinterpret_cast<const float2*>(rowsum), gamma,
       reinterpret_cast<__nv_bfloat16*>(hn), reinterpret_cast<__nv_bfloat16*>(hn_copy_bf16), reinterpret_cast<float2*>(stats),
       reinterpret_cast<uint8_t*>(keep_bits), M, F, Fp,
@@ -377,9 +385,9 @@ int omlm_ffn_mid_bwd(const void* dhn, const void* hn, const void* u, const float
   const long M = static_cast<long>(B) * N;
   auto stats_kern = ffn_mid_bwd_stats_kernel;
   auto walk_kern = act_f16 ? ffn_mid_bwd_walk_kernel<true> : ffn_mid_bwd_walk_kernel<false>;
-  stats_kern<<<static_cast<int>((M + 7) / 8), 256, 0, st>>>(
+  OMLM_KLAUNCH((stats_kern), static_cast<int>((M + 7) / 8), 256, 0, st, 
       reinterpret_cast<const __nv_bfloat16*>(dhn), reinterpret_cast<const __nv_bfloat16*>(hn), gamma,
-      reinterpret_cast<float2*>(rowstat_scratch), M, F, Fp, drop_p, a.keep_bits);
+      reinterpret_cast<float2*>(rowstat_scratch), M, F, Fp, drop_p, a.keep_bits, dgamma, dconv_w);
   OMLM_LAUNCH_CHECK();
   static bool configured = false;
   if (!configured) {
@@ -388,7 +396,7 @@ int omlm_ffn_mid_bwd(const void* dhn, const void* hn, const void* u, const float
     configured = true;
   }
   dim3 grid(B * ((N + kTileRows - 1) / kTileRows), Fp / 128);
-  walk_kern<<<grid, kTileThreads, kTileSmem, st>>>(a, reinterpret_cast<const __nv_bfloat16*>(dhn),
+  OMLM_KLAUNCH((walk_kern), grid, kTileThreads, kTileSmem, st, a, reinterpret_cast<const __nv_bfloat16*>(dhn),
                                                                 reinterpret_cast<const float2*>(stats),
                                                                 reinterpret_cast<const float2*>(rowstat_scratch),
                                                                 reinterpret_cast<__nv_bfloat16*>(du), dgamma, dconv_w);

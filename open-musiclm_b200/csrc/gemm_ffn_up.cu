@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(kFuThreads, 1)
 gemm_ffn_up_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    __nv_bfloat16* __restrict__ u_out, __nv_bfloat16* __restrict__ h_out, float* __restrict__ rowsum,
                    const float* __restrict__ conv_w, int M, int Nseq, int K, int Fp) {
+  pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kFuOffBar);
@@ -62,6 +63,7 @@ gemm_ffn_up_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // private set-up done: from here on global memory written by the previous kernel is touched
 
   if (warp == 0) {
     if (lane == 0) {   // ---------------------------------------------------------------- TMA producer
@@ -260,7 +262,7 @@ extern "C" int omlm_gemm_ffn_up(const void* xn, const void* w1_packed, const flo
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
   if (m_tiles * n_tiles < grid) grid = m_tiles * n_tiles;
   auto kern = act_f16 ? gemm_ffn_up_kernel<true> : gemm_ffn_up_kernel<false>;
-  kern<<<grid, kFuThreads, kFuSmem, reinterpret_cast<cudaStream_t>(stream)>>>(
+  OMLM_KLAUNCH((kern), grid, kFuThreads, kFuSmem, reinterpret_cast<cudaStream_t>(stream), 
       tmA, tmB, reinterpret_cast<__nv_bfloat16*>(u_out), reinterpret_cast<__nv_bfloat16*>(h_out), rowsum, conv_w_packed, M,
       Nseq, K, Fp);
   OMLM_LAUNCH_CHECK();

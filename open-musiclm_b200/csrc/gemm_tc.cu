@@ -3,7 +3,12 @@
 //   warp 0      : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1      : tcgen05.mma issuer (one elected lane), accumulators in TMEM, double-buffered
 //   warps 2..9  : epilogue (tcgen05.ld TMEM -> registers -> fused epilogue -> global); two warps per TMEM lane
-//                 quarter (= per SM sub-partition), each draining one half of the tile's columns
+//                 quarter (= per SM sub-partition), each draining one half of the tile's columns.
+//                 Dense outputs (no row remapping, no split-K) leave through shared memory: every warp stages its
+//                 32-row x 128-byte chunk in a 128B-swizzled buffer (bank-conflict free with lane = row) and one lane
+//                 issues a TMA store, so the global writes are whole 128-byte rows instead of 32 scattered 16-byte
+//                 pieces per instruction; a residual / beta = 1 addend arrives the same way (TMA loads into the warp's
+//                 buffers, two chunks ahead, crossing tile boundaries).
 //
 // Operand majors are template parameters so that one kernel serves the forward projections
 // (A K-major, B K-major: nn.Linear weights are [out,in]), the data-gradient GEMMs (B MN-major: the
@@ -15,13 +20,13 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include "../../include/omlm_b200.h"
+#include <stdlib.h>
 
 namespace omlm {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int kGemmThreads = 320;
-constexpr int kSmemBudget = 196608;  // ring bytes
 
 struct EpiParams {
   void* out;            // bf16 or fp32
@@ -35,30 +40,39 @@ struct EpiParams {
   int row_split;  // >0: rows are two halves of row_split, each with row_valid live rows; <0: interleaved GEGLU groups of 128
   int row_valid;
   int n_valid;    // columns >= n_valid are dropped
+  int tma_mode;   // 0: per-thread global stores; 1: TMA store; 2: TMA addend in place + TMA store; 3: TMA addend prefetched (2 buffers) + TMA store
 };
+
+constexpr int kEpiWarps = 8;
+constexpr int kEpiBuf = 4096;     // one staging buffer: 32 rows x 128 bytes, 128B-swizzled
+__host__ __device__ constexpr int epi_bufs_per_warp(int tma_mode) { return tma_mode == 3 ? 3 : (tma_mode != 0 ? 1 : 0); }
 
 template <int BN>
 struct GemmSmem {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = kSmemBudget / kStageBytes;
+  static constexpr int kMaxStages = 8;
 };
 
 template <int BN, int A_MN, int B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const EpiParams ep, const int M, const int N, const int K, const int splits, const uint32_t idesc) {
+                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAdd,
+                 const EpiParams ep, const int M, const int N, const int K, const int splits, const uint32_t idesc,
+                 const int kStages) {
+  pdl_launch_dependents();
   using S = GemmSmem<BN>;
-  constexpr int kStages = S::kStages;
   extern __shared__ uint8_t smem_raw[];
   // 1024B alignment is required by the 128B swizzle atoms.
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tfull_bar = empty_bar + kStages;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* staging = smem + kStages * S::kStageBytes;                       // epilogue staging buffers (1024B aligned)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kEpiWarps * epi_bufs_per_warp(ep.tma_mode) * kEpiBuf);
+  uint64_t* empty_bar = full_bar + S::kMaxStages;
+  uint64_t* tfull_bar = empty_bar + S::kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* add_bar = tempty_bar + 2;                                       // [kEpiWarps][2] addend chunks landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(add_bar + 2 * kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -72,6 +86,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (ep.tma_mode != 0) tma_prefetch_desc(&tmOut);
+    if (ep.tma_mode >= 2) tma_prefetch_desc(&tmAdd);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -83,6 +99,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_init(&tfull_bar[i], 1);
         mbar_init(&tempty_bar[i], 8);
       }
+      for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&add_bar[i], 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -92,6 +109,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // private set-up done: from here on global memory written by the previous kernel is touched
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -163,6 +181,121 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
+  } else if (ep.tma_mode != 0) {
+    // ------------------------------------------------------------------ epilogue warps, shared-memory staged (TMA)
+    // The warp walks its chunks (32 rows x 128 bytes of output: 32 fp32 or 64 bf16 columns) as ONE sequence across
+    // tiles, so that residual chunks can be requested ahead of the tile they belong to.
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
+    const int ew = warp - 2, half = ew >> 2;      // half: which half of the tile's columns
+    const int n_in = ep.tma_mode == 3 ? 2 : (ep.tma_mode == 2 ? 1 : 0);
+    const bool inplace = ep.tma_mode == 2;
+    uint8_t* my = staging + ew * epi_bufs_per_warp(ep.tma_mode) * kEpiBuf;
+    uint8_t* out_buf = my + (inplace ? 0 : n_in) * kEpiBuf;
+    uint64_t* in_bar = add_bar + ew * 2;
+    const int CW = ep.out_f32 ? 32 : 64;          // columns per chunk
+    const int cpt = (BN / 2) / CW;                // chunks per tile for this warp
+    const int my_tiles = blockIdx.x < work_total ? (work_total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int total = my_tiles * cpt;
+    const uint32_t sw = static_cast<uint32_t>(lane & 7) << 4;
+    const uint32_t row_off = static_cast<uint32_t>(lane) * 128;
+    auto coords = [&](int g, int& row0, int& col0) {
+      const int t = g / cpt, c = g - t * cpt;
+      const int tile = blockIdx.x + t * gridDim.x;          // splits == 1 on this path
+      const int n_blk = tile % n_tiles, m_blk = tile / n_tiles;
+      row0 = m_blk * BM + quarter * 32;
+      col0 = n_blk * BN + half * (BN / 2) + c * CW;
+      return row0 < M && col0 < ep.n_valid;
+    };
+    auto issue_load = [&](int g) {                          // lane 0 only
+      int row0, col0;
+      if (g < total && coords(g, row0, col0)) {
+        const int b = g % n_in;
+        mbar_expect_tx(&in_bar[b], kEpiBuf);
+        tma_load_2d(my + b * kEpiBuf, &tmAdd, &in_bar[b], col0, row0);
+      }
+    };
+    if (n_in == 2 && lane == 0) { issue_load(0); issue_load(1); }
+    int acc = 0;
+    uint32_t acc_phase = 0, in_phase = 0;
+    for (int g = 0; g < total; ++g) {
+      const int c = g % cpt;
+      int row0, col0;
+      const bool live = coords(g, row0, col0);
+      if (c == 0) {
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+      }
+      const uint8_t* in_buf = my + (n_in ? (g % n_in) : 0) * kEpiBuf;
+      if (n_in != 0) {
+        if (inplace) {        // one buffer: the previous chunk's store must have read it before the addend overwrites it
+          if (lane == 0) { tma_store_wait_read<0>(); issue_load(g); }
+          __syncwarp();
+        }
+        if (live) {
+          const int b = g % n_in;
+          mbar_wait(&in_bar[b], (in_phase >> b) & 1);
+          in_phase ^= 1u << b;
+        }
+      }
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * (BN / 2) + c * CW;
+      uint32_t r0[32], r1[32];
+      tmem_ld32(taddr, r0);
+      if (!ep.out_f32) tmem_ld32(taddr + 32, r1);
+      tmem_ld_wait();
+      if (c == cpt - 1) {     // accumulator drained (for this warp): hand the TMEM buffer back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (live) {
+        uint4 q[8];
+        if (ep.out_f32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 v = make_float4(__uint_as_float(r0[4 * j]) * ep.alpha, __uint_as_float(r0[4 * j + 1]) * ep.alpha,
+                                   __uint_as_float(r0[4 * j + 2]) * ep.alpha, __uint_as_float(r0[4 * j + 3]) * ep.alpha);
+            if (n_in != 0) {
+              const float4 a = *reinterpret_cast<const float4*>(in_buf + row_off + ((static_cast<uint32_t>(j) << 4) ^ sw));
+              v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+            }
+            q[j] = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            q[j] = make_uint4(pack_bf16x2(__uint_as_float(r0[8 * j]) * ep.alpha, __uint_as_float(r0[8 * j + 1]) * ep.alpha),
+                              pack_bf16x2(__uint_as_float(r0[8 * j + 2]) * ep.alpha, __uint_as_float(r0[8 * j + 3]) * ep.alpha),
+                              pack_bf16x2(__uint_as_float(r0[8 * j + 4]) * ep.alpha, __uint_as_float(r0[8 * j + 5]) * ep.alpha),
+                              pack_bf16x2(__uint_as_float(r0[8 * j + 6]) * ep.alpha, __uint_as_float(r0[8 * j + 7]) * ep.alpha));
+            q[4 + j] = make_uint4(pack_bf16x2(__uint_as_float(r1[8 * j]) * ep.alpha, __uint_as_float(r1[8 * j + 1]) * ep.alpha),
+                                  pack_bf16x2(__uint_as_float(r1[8 * j + 2]) * ep.alpha, __uint_as_float(r1[8 * j + 3]) * ep.alpha),
+                                  pack_bf16x2(__uint_as_float(r1[8 * j + 4]) * ep.alpha, __uint_as_float(r1[8 * j + 5]) * ep.alpha),
+                                  pack_bf16x2(__uint_as_float(r1[8 * j + 6]) * ep.alpha, __uint_as_float(r1[8 * j + 7]) * ep.alpha));
+          }
+        }
+        if (!inplace) {
+          __syncwarp();       // every lane has read its addend row: the buffer may be refilled, two chunks ahead
+          if (lane == 0) {
+            if (n_in != 0) issue_load(g + n_in);
+            tma_store_wait_read<0>();       // the previous chunk's store has read the staging buffer
+          }
+          __syncwarp();
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(out_buf + row_off + ((static_cast<uint32_t>(j) << 4) ^ sw)) = q[j];
+        fence_proxy_async();   // generic-proxy stores -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmOut, out_buf, col0, row0);
+          tma_store_commit();
+        }
+      } else if (n_in != 0 && !inplace) {
+        if (lane == 0) issue_load(g + n_in);
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
   } else {
     // ------------------------------------------------------------------ epilogue warps
     const int quarter = warp & 3;  // TMEM lane quarter this warp may read
@@ -292,15 +425,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+constexpr int kMaxDynSmem = 232448;      // 227 KB per CTA on sm_100
+constexpr int kBarrierBytes = 512;
+
 template <int BN, int A_MN, int B_MN>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams& ep, int M,
-                       int N, int K, int splits, int max_ctas, int a_f16, int b_f16, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmAdd,
+                       const EpiParams& ep, int M, int N, int K, int splits, int max_ctas, int a_f16, int b_f16,
+                       cudaStream_t stream) {
   using S = GemmSmem<BN>;
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
-  const int smem_bytes = S::kStages * S::kStageBytes + 1024 + 256;
+  // shared memory: operand ring | epilogue staging | barriers.  The ring takes what the staging buffers leave.
+  const int staging = kEpiWarps * epi_bufs_per_warp(ep.tma_mode) * kEpiBuf;
+  int stages = (kMaxDynSmem - 1024 - kBarrierBytes - staging) / S::kStageBytes;
+  if (stages > 6) stages = 6;
+  const int smem_bytes = stages * S::kStageBytes + staging + kBarrierBytes + 1024;
   static bool configured = false;
   if (!configured) {
-    OMLM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    OMLM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     configured = true;
   }
   const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
@@ -312,9 +453,18 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Epi
   uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
   if (a_f16) idesc &= ~(7u << 7);
   if (b_f16) idesc &= ~(7u << 10);
-  kern<<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmB, ep, M, N, K, splits, idesc);
+  OMLM_KLAUNCH((kern), grid, kGemmThreads, smem_bytes, stream, tmA, tmB, tmOut, tmAdd, ep, M, N, K, splits, idesc, stages);
   OMLM_LAUNCH_CHECK();
   return 0;
+}
+
+static bool tma_epilogue_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("OMLM_GEMM_TMA_EPI");       // diagnostics: 0 = per-thread global stores everywhere
+    on = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
 }
 
 }  // namespace omlm
@@ -353,14 +503,29 @@ extern "C" int omlm_gemm16(const void* A, int a_f16, int a_mn_major, long lda, c
   ep.vec_ok = ((ldo * esz) % 16 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
               (addend == nullptr || ((ldadd * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(addend) & 15) == 0));
   ep.row_split = row_split; ep.row_valid = row_valid; ep.n_valid = n_valid;
+  // dense outputs leave through shared memory + TMA (see the kernel header); everything that remaps rows, reduces
+  // atomically or is not 16-byte aligned keeps the per-thread path
+  ep.tma_mode = 0;
+  CUtensorMap tmOut = tmA, tmAdd = tmA;     // placeholders when unused (never dereferenced)
+  if (tma_epilogue_enabled() && splits == 1 && row_split == 0 && ep.vec_ok && (addend == nullptr || out_f32)) {
+    const uint32_t cw = out_f32 ? 32 : 64;
+    rc = make_tmap_2d(&tmOut, static_cast<int>(esz), out, (uint64_t)n_valid, (uint64_t)M, (uint64_t)ldo * esz, cw, 32);
+    if (rc) return rc;
+    ep.tma_mode = 1;
+    if (addend != nullptr) {
+      rc = make_tmap_2d(&tmAdd, 4, addend, (uint64_t)n_valid, (uint64_t)M, (uint64_t)ldadd * 4, 32, 32);
+      if (rc) return rc;
+      ep.tma_mode = block_n == 128 ? 3 : 2;   // 128-wide tiles (short K, HBM-bound residual GEMMs): deep prefetch
+    }
+  }
   const int key = (block_n == 256 ? 4 : 0) | (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
   switch (key) {
-    case 0: return launch_gemm<128, 0, 0>(tmA, tmB, ep, M, N, K, splits, max_ctas, a_f16, b_f16, stream);
-    case 1: return launch_gemm<128, 0, 1>(tmA, tmB, ep, M, N, K, splits, max_ctas, a_f16, b_f16, stream);
-    case 3: return launch_gemm<128, 1, 1>(tmA, tmB, ep, M, N, K, splits, max_ctas, a_f16, b_f16, stream);
-    case 4: return launch_gemm<256, 0, 0>(tmA, tmB, ep, M, N, K, splits, max_ctas, a_f16, b_f16, stream);
-    case 5: return launch_gemm<256, 0, 1>(tmA, tmB, ep, M, N, K, splits, max_ctas, a_f16, b_f16, stream);
-    case 7: return launch_gemm<256, 1, 1>(tmA, tmB, ep, M, N, K, splits, max_ctas, a_f16, b_f16, stream);
+    case 0: return launch_gemm<128, 0, 0>(tmA, tmB, tmOut, tmAdd, ep, M, N, K, splits, max_ctas, a_f16, b_f16, stream);
+    case 1: return launch_gemm<128, 0, 1>(tmA, tmB, tmOut, tmAdd, ep, M, N, K, splits, max_ctas, a_f16, b_f16, stream);
+    case 3: return launch_gemm<128, 1, 1>(tmA, tmB, tmOut, tmAdd, ep, M, N, K, splits, max_ctas, a_f16, b_f16, stream);
+    case 4: return launch_gemm<256, 0, 0>(tmA, tmB, tmOut, tmAdd, ep, M, N, K, splits, max_ctas, a_f16, b_f16, stream);
+    case 5: return launch_gemm<256, 0, 1>(tmA, tmB, tmOut, tmAdd, ep, M, N, K, splits, max_ctas, a_f16, b_f16, stream);
+    case 7: return launch_gemm<256, 1, 1>(tmA, tmB, tmOut, tmAdd, ep, M, N, K, splits, max_ctas, a_f16, b_f16, stream);
     default:
       set_last_error("gemm: operand majors (a_mn=%d, b_mn=%d) not instantiated", a_mn_major, b_mn_major);
       return 1;

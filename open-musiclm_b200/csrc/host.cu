@@ -5,6 +5,7 @@
 #include <cudaTypedefs.h>
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include <mutex>
 
 namespace omlm {
@@ -50,6 +51,24 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t dim0, uint64_
   return 0;
 }
 
+int make_tmap_2d(CUtensorMap* out, int elem_bytes, const void* gptr, uint64_t dim0, uint64_t dim1, uint64_t pitch_bytes,
+                 uint32_t box0, uint32_t box1) {
+  std::call_once(g_encode_once, resolve_encode);
+  OMLM_CHECK_ARG(g_encode != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  OMLM_CHECK_ARG(elem_bytes == 2 || elem_bytes == 4, "make_tmap_2d: element size %d", elem_bytes);
+  OMLM_CHECK_ARG((reinterpret_cast<uintptr_t>(gptr) & 15) == 0 && (pitch_bytes & 15) == 0, "TMA base / pitch must be 16B aligned");
+  OMLM_CHECK_ARG(box0 * elem_bytes == 128 && box1 >= 1 && box1 <= 256, "bad TMA box %u x %u", box0, box1);
+  cuuint64_t dims[2] = {dim0, dim1};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                        const_cast<void*>(gptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  OMLM_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
 int make_tmap_bf16_3d(CUtensorMap* out, const void* gptr, uint64_t dim0, uint64_t dim1, uint64_t dim2,
                       uint64_t pitch1_bytes, uint64_t pitch2_bytes, uint32_t box0, uint32_t box1) {
   std::call_once(g_encode_once, resolve_encode);
@@ -66,6 +85,15 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* gptr, uint64_t dim0, uint64_
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   OMLM_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r);
   return 0;
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("OMLM_PDL");       // OMLM_PDL=1 turns programmatic dependent launch on (see common.cuh)
+    on = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return on == 1;
 }
 
 int num_sms() {

@@ -14,6 +14,7 @@ __global__ void __launch_bounds__(256)
 ce_fwd_bwd_kernel(const float* __restrict__ logits, long ld, const int* __restrict__ labels, int label_stride,
                   int rows, int C, int ignore_index, float grad_scale, __nv_bfloat16* __restrict__ dlogits,
                   long ldd, int Cp, float* __restrict__ loss_acc) {
+  pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   float my_loss = 0.f, my_cnt = 0.f;
@@ -73,7 +74,7 @@ extern "C" int omlm_cross_entropy(const float* logits, long ld, const int* label
                                   int Cp, float* loss_acc, void* stream) {
   using namespace omlm;
   OMLM_CHECK_ARG(rows > 0 && C > 0 && C <= 32 * kCeMaxPerLane && Cp <= 32 * kCeMaxPerLane, "cross_entropy: unsupported C=%d", C);
-  ce_fwd_bwd_kernel<<<(rows + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  OMLM_KLAUNCH((ce_fwd_bwd_kernel), (rows + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       logits, ld, labels, label_stride, rows, C, ignore_index, grad_scale,
       reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), ldd, Cp, loss_acc);
   OMLM_LAUNCH_CHECK();

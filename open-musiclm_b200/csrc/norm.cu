@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(kNormThreads)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                      __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ ycopy, __nv_bfloat16* __restrict__ xraw,
                      float2* __restrict__ stats, const int* __restrict__ dest_row, int M, int D, int y_f16) {
+  pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (kNormThreads / 32) + warp;
   if (row >= M) return;
@@ -96,6 +97,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
                      const int* __restrict__ src_row, float* __restrict__ dx,
                      __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, int M, int D,
                      int rows_per_block) {
+  pdl_prologue();
   constexpr int kRow = NCHUNK * 128;                 // padded row length in elements
   constexpr int kStage = kRow * 12;                  // x fp32 | dres fp32 | dy bf16 | draw bf16
   extern __shared__ __align__(16) uint8_t lsm[];
@@ -217,6 +219,7 @@ __global__ void __launch_bounds__(256)
 qk_l2norm_fwd_kernel(const __nv_bfloat16* __restrict__ q_raw, const __nv_bfloat16* __restrict__ kv_raw,
                      const float* __restrict__ q_scale, const float* __restrict__ k_scale,
                      __nv_bfloat16* __restrict__ qn, __nv_bfloat16* __restrict__ kvn, int M, int h) {
+  pdl_prologue();
   const long long gvec = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
   const int sub = threadIdx.x & 7;
   const int per_row = h + 2;
@@ -269,6 +272,7 @@ qk_l2norm_bwd_kernel(const float* __restrict__ dqn, const float* __restrict__ dk
                      const float* __restrict__ q_scale, const float* __restrict__ k_scale,
                      __nv_bfloat16* __restrict__ dq_raw, __nv_bfloat16* __restrict__ dkv_raw,
                      float* __restrict__ dq_scale, float* __restrict__ dk_scale, int M, int h) {
+  pdl_prologue();
   __shared__ float sds[2][64];
   if (threadIdx.x < 128) sds[threadIdx.x >> 6][threadIdx.x & 63] = 0.f;
   __syncthreads();
@@ -361,7 +365,7 @@ template <int NCHUNK>
 static int launch_ln_fwd(const float* x, const float* gamma, __nv_bfloat16* y, __nv_bfloat16* ycopy, __nv_bfloat16* xraw,
                          float2* stats, const int* dest_row, int M, int D, int y_f16, cudaStream_t st) {
   const int rows_per_block = kNormThreads / 32;
-  layernorm_fwd_kernel<NCHUNK><<<(M + rows_per_block - 1) / rows_per_block, kNormThreads, 0, st>>>(
+  OMLM_KLAUNCH((layernorm_fwd_kernel<NCHUNK>), (M + rows_per_block - 1) / rows_per_block, kNormThreads, 0, st, 
       x, gamma, y, ycopy, xraw, stats, dest_row, M, D, y_f16);
   OMLM_LAUNCH_CHECK();
   return 0;
@@ -384,7 +388,7 @@ static int launch_ln_bwd(const __nv_bfloat16* dy, const float* x, const float2* 
   int rows_per_block = (M + blocks - 1) / blocks;
   if (rows_per_block < WARPS) rows_per_block = WARPS;
   blocks = (M + rows_per_block - 1) / rows_per_block;
-  layernorm_bwd_kernel<NCHUNK, WARPS><<<blocks, WARPS * 32, smem, st>>>(dy, x, stats, gamma, dres, draw, src_row, dx,
+  OMLM_KLAUNCH((layernorm_bwd_kernel<NCHUNK, WARPS>), blocks, WARPS * 32, smem, st, dy, x, stats, gamma, dres, draw, src_row, dx,
                                                                        dx_bf16, dgamma, M, D, rows_per_block);
   OMLM_LAUNCH_CHECK();
   return 0;
@@ -435,7 +439,7 @@ int omlm_qk_l2norm_fwd(const void* q_raw, const void* kv_raw, const float* q_sca
   OMLM_CHECK_ARG(M > 0 && heads > 0, "qk_l2norm_fwd: bad shape");
   const long long total = static_cast<long long>(M) * (heads + 2);
   const int blocks = static_cast<int>((total * 8 + 255) / 256);
-  qk_l2norm_fwd_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  OMLM_KLAUNCH((qk_l2norm_fwd_kernel), blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(q_raw), reinterpret_cast<const __nv_bfloat16*>(kv_raw), q_scale,
       k_scale, reinterpret_cast<__nv_bfloat16*>(qn), reinterpret_cast<__nv_bfloat16*>(kvn), M, heads);
   OMLM_LAUNCH_CHECK();
@@ -451,7 +455,7 @@ int omlm_qk_l2norm_bwd(const float* dqn, const float* dkvn, const void* q_raw, c
   long long blocks = (total + 31) / 32;
   const long long cap = static_cast<long long>(num_sms()) * 8;
   if (blocks > cap) blocks = cap;
-  qk_l2norm_bwd_kernel<<<static_cast<int>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  OMLM_KLAUNCH((qk_l2norm_bwd_kernel), static_cast<int>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       dqn, dkvn, reinterpret_cast<const __nv_bfloat16*>(q_raw), reinterpret_cast<const __nv_bfloat16*>(kv_raw),
       q_scale, k_scale, reinterpret_cast<__nv_bfloat16*>(dq_raw), reinterpret_cast<__nv_bfloat16*>(dkv_raw),
       dq_scale, dk_scale, M, heads);

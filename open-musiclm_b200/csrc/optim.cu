@@ -14,6 +14,7 @@ namespace omlm {
 // acc[0] (double) += sum (g * prescale)^2
 __global__ void __launch_bounds__(512)
 sumsq_kernel(const float* __restrict__ g, long n, float prescale, double* __restrict__ acc) {
+  pdl_prologue();
   float s = 0.f;
   const long n4 = n >> 2;
   const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -38,6 +39,7 @@ sumsq_kernel(const float* __restrict__ g, long n, float prescale, double* __rest
 __global__ void __launch_bounds__(512)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              long n, long n_decay, const float* __restrict__ hyper, const double* __restrict__ sumsq) {
+  pdl_prologue();
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
   const float bc1 = hyper[5], bc2 = hyper[6], max_norm = hyper[7], prescale = hyper[8];
   float coef = prescale;
@@ -110,6 +112,7 @@ __device__ __forceinline__ void pack_quad(long i, const float* __restrict__ src,
 template <typename OutT>
 __global__ void pack_kernel(const float* __restrict__ src, long src_ld, int rows_valid, int cols_valid,
                             OutT* __restrict__ dst, long dst_ld, int rows_p, int cols_p, int split_dst, int split_src) {
+  pdl_prologue();
   const long total = static_cast<long>(rows_p) * ((cols_p + 3) >> 2);
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x)
     pack_quad<OutT>(i, src, src_ld, rows_valid, cols_valid, dst, dst_ld, cols_p, split_dst, split_src);
@@ -119,6 +122,7 @@ __global__ void pack_kernel(const float* __restrict__ src, long src_ld, int rows
 // 256 quads and blocks stride over the concatenated unit list (45 small launches -> 1 bandwidth-bound pass).
 constexpr int kPackMaxJobs = 512;
 __global__ void __launch_bounds__(256) pack_multi_kernel(const omlm_pack_job* __restrict__ jobs, int njobs, long total_units) {
+  pdl_prologue();
   __shared__ long starts[kPackMaxJobs + 1];
   for (int j = threadIdx.x; j < njobs; j += blockDim.x) starts[j] = jobs[j].unit_start;
   if (threadIdx.x == 0) starts[njobs] = total_units;
@@ -140,6 +144,7 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const omlm_pack_job* __
 __global__ void unpack_add_kernel(const float* __restrict__ packed, long p_ld, int rows_p, int cols_p,
                                   float* __restrict__ dst, long dst_ld, int rows_valid, int cols_valid,
                                   int split_dst, int split_src) {
+  pdl_prologue();
   const long total = static_cast<long>(rows_p) * cols_p;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const int r = static_cast<int>(i / cols_p), c = static_cast<int>(i - static_cast<long>(r) * cols_p);
@@ -159,7 +164,7 @@ int omlm_grad_sumsq(const float* g, long n, float prescale, double* acc, void* s
   OMLM_CHECK_ARG(n > 0, "grad_sumsq: empty");
   OMLM_CHECK_ARG((reinterpret_cast<uintptr_t>(g) & 15) == 0, "grad_sumsq: arena must be 16B aligned");
   const int blocks = static_cast<int>(std::min<long>((n / 4 + 511) / 512 + 1, static_cast<long>(num_sms()) * 4));
-  sumsq_kernel<<<blocks, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(g, n, prescale, acc);
+  OMLM_KLAUNCH((sumsq_kernel), blocks, 512, 0, reinterpret_cast<cudaStream_t>(stream), g, n, prescale, acc);
   OMLM_LAUNCH_CHECK();
   return 0;
 }
@@ -169,7 +174,7 @@ int omlm_adamw_step(float* p, const float* g, float* m, float* v, long n, long n
   using namespace omlm;
   OMLM_CHECK_ARG(n > 0 && n_decay >= 0 && n_decay <= n, "adamw_step: bad sizes");
   const int blocks = static_cast<int>(std::min<long>((n + 511) / 512, static_cast<long>(num_sms()) * 8));
-  adamw_kernel<<<blocks, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, n_decay, hyper, sumsq);
+  OMLM_KLAUNCH((adamw_kernel), blocks, 512, 0, reinterpret_cast<cudaStream_t>(stream), p, g, m, v, n, n_decay, hyper, sumsq);
   OMLM_LAUNCH_CHECK();
   return 0;
 }
@@ -183,11 +188,11 @@ int omlm_pack(const float* src, long src_ld, int rows_valid, int cols_valid, voi
   auto st = reinterpret_cast<cudaStream_t>(stream);
   OMLM_CHECK_ARG(dst_fmt == kFmtBF16 || dst_fmt == kFmtF32 || dst_fmt == kFmtF16, "pack: dst_fmt must be 0 (bf16), 1 (fp32) or 2 (fp16)");
   if (dst_fmt == kFmtF32)
-    pack_kernel<float><<<blocks, 256, 0, st>>>(src, src_ld, rows_valid, cols_valid, reinterpret_cast<float*>(dst), dst_ld, rows_p, cols_p, split_dst, split_src);
+    OMLM_KLAUNCH((pack_kernel<float>), blocks, 256, 0, st, src, src_ld, rows_valid, cols_valid, reinterpret_cast<float*>(dst), dst_ld, rows_p, cols_p, split_dst, split_src);
   else if (dst_fmt == kFmtF16)
-    pack_kernel<__half><<<blocks, 256, 0, st>>>(src, src_ld, rows_valid, cols_valid, reinterpret_cast<__half*>(dst), dst_ld, rows_p, cols_p, split_dst, split_src);
+    OMLM_KLAUNCH((pack_kernel<__half>), blocks, 256, 0, st, src, src_ld, rows_valid, cols_valid, reinterpret_cast<__half*>(dst), dst_ld, rows_p, cols_p, split_dst, split_src);
   else
-    pack_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(src, src_ld, rows_valid, cols_valid, reinterpret_cast<__nv_bfloat16*>(dst), dst_ld, rows_p, cols_p, split_dst, split_src);
+    OMLM_KLAUNCH((pack_kernel<__nv_bfloat16>), blocks, 256, 0, st, src, src_ld, rows_valid, cols_valid, reinterpret_cast<__nv_bfloat16*>(dst), dst_ld, rows_p, cols_p, split_dst, split_src);
   OMLM_LAUNCH_CHECK();
   return 0;
 }
@@ -196,7 +201,7 @@ int omlm_pack_multi(const omlm_pack_job* jobs_device, int njobs, long total_unit
   using namespace omlm;
   OMLM_CHECK_ARG(jobs_device != nullptr && njobs > 0 && njobs <= kPackMaxJobs && total_units > 0, "pack_multi: need 1..%d jobs per table (got %d)", kPackMaxJobs, njobs);
   const int blocks = static_cast<int>(std::min<long>(total_units, static_cast<long>(num_sms()) * 16));
-  pack_multi_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(jobs_device, njobs, total_units);
+  OMLM_KLAUNCH((pack_multi_kernel), blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream), jobs_device, njobs, total_units);
   OMLM_LAUNCH_CHECK();
   return 0;
 }
@@ -207,7 +212,7 @@ int omlm_unpack_add(const float* packed, long p_ld, int rows_p, int cols_p, floa
   OMLM_CHECK_ARG(rows_p > 0 && cols_p > 0, "unpack_add: empty");
   const long total = static_cast<long>(rows_p) * cols_p;
   const int blocks = static_cast<int>(std::min<long>((total + 255) / 256, static_cast<long>(num_sms()) * 8));
-  unpack_add_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(packed, p_ld, rows_p, cols_p, dst, dst_ld, rows_valid, cols_valid, split_dst, split_src);
+  OMLM_KLAUNCH((unpack_add_kernel), blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream), packed, p_ld, rows_p, cols_p, dst, dst_ld, rows_valid, cols_valid, split_dst, split_src);
   OMLM_LAUNCH_CHECK();
   return 0;
 }

@@ -16,6 +16,7 @@ sgemm_small_kernel(const float* __restrict__ A, long sa_m, long sa_k, const floa
                    long sb_k, long sb_n, float* __restrict__ C, long sc_m, long sc_n,
                    float* __restrict__ Z, const float* __restrict__ bias, int M, int N, int K, int act,
                    int accumulate) {
+  pdl_prologue();
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[16][64 + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -76,6 +77,7 @@ sgemm_small_kernel(const float* __restrict__ A, long sa_m, long sa_k, const floa
 // dZ = dA * silu'(z),  silu'(z) = s + z*s*(1-s), s = sigmoid(z)
 __global__ void silu_bwd_kernel(const float* __restrict__ dA, const float* __restrict__ Zp,
                                 float* __restrict__ dZ, __nv_bfloat16* __restrict__ dZ_bf16, long n) {
+  pdl_prologue();
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
     const float z = Zp[i];
@@ -89,6 +91,7 @@ __global__ void silu_bwd_kernel(const float* __restrict__ dA, const float* __res
 // out[n] (+)= sum_m X[m*s_m + n*s_n]
 __global__ void colsum_kernel(const float* __restrict__ X, long s_m, long s_n, float* __restrict__ out,
                               int M, int N, int accumulate) {
+  pdl_prologue();
   const int n = blockIdx.x;
   float s = 0.f;
   for (int m = threadIdx.x; m < M; m += blockDim.x) s += X[m * s_m + n * s_n];
@@ -108,6 +111,7 @@ __global__ void colsum_kernel(const float* __restrict__ X, long s_m, long s_n, f
 // A3 . W3^T = a_hi w_hi + a_hi w_lo + a_lo w_hi  ~  a . w  to ~2^-16 relative, accumulated in fp32 by tcgen05.
 __global__ void split3_kernel(const float* __restrict__ src, long src_ld, __nv_bfloat16* __restrict__ dst, int R,
                               int C, int weight_mode) {
+  pdl_prologue();
   const long total = static_cast<long>(R) * C;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const int r = static_cast<int>(i / C), c = static_cast<int>(i - static_cast<long>(r) * C);
@@ -123,6 +127,7 @@ __global__ void split3_kernel(const float* __restrict__ src, long src_ld, __nv_b
 
 // z += bias (in place);  a = silu(z)
 __global__ void bias_silu_kernel(float* __restrict__ z, const float* __restrict__ bias, float* __restrict__ a, int R, int C) {
+  pdl_prologue();
   const long total = static_cast<long>(R) * C;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % C);
@@ -133,6 +138,7 @@ __global__ void bias_silu_kernel(float* __restrict__ z, const float* __restrict_
 }
 
 __global__ void arange_kernel(float* out, int n) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = static_cast<float>(i);
 }
@@ -152,7 +158,7 @@ int omlm_sgemm_small(const float* A, long sa_m, long sa_k, const float* B, long 
     const int ctas = static_cast<int>(grid.x * grid.y);
     if (ctas < 64) grid.z = static_cast<unsigned>(std::max(1, std::min((K + 31) / 32, 256 / ctas)));
   }
-  sgemm_small_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  OMLM_KLAUNCH((sgemm_small_kernel), grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       A, sa_m, sa_k, B, sb_k, sb_n, C, sc_m, sc_n, Z, bias, M, N, K, act, accumulate);
   OMLM_LAUNCH_CHECK();
   return 0;
@@ -162,7 +168,7 @@ int omlm_silu_bwd(const float* dA, const float* Z, float* dZ, void* dZ_bf16, lon
   using namespace omlm;
   OMLM_CHECK_ARG(n > 0, "silu_bwd: empty");
   const int blocks = static_cast<int>(std::min<long>((n + 255) / 256, 4096));
-  silu_bwd_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dA, Z, dZ, reinterpret_cast<__nv_bfloat16*>(dZ_bf16), n);
+  OMLM_KLAUNCH((silu_bwd_kernel), blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream), dA, Z, dZ, reinterpret_cast<__nv_bfloat16*>(dZ_bf16), n);
   OMLM_LAUNCH_CHECK();
   return 0;
 }
@@ -170,7 +176,7 @@ int omlm_silu_bwd(const float* dA, const float* Z, float* dZ, void* dZ_bf16, lon
 int omlm_colsum(const float* X, long s_m, long s_n, float* out, int M, int N, int accumulate, void* stream) {
   using namespace omlm;
   OMLM_CHECK_ARG(M > 0 && N > 0, "colsum: empty");
-  colsum_kernel<<<N, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(X, s_m, s_n, out, M, N, accumulate);
+  OMLM_KLAUNCH((colsum_kernel), N, 256, 0, reinterpret_cast<cudaStream_t>(stream), X, s_m, s_n, out, M, N, accumulate);
   OMLM_LAUNCH_CHECK();
   return 0;
 }
@@ -180,7 +186,7 @@ int omlm_split3_bf16(const float* src, long src_ld, void* dst, int R, int C, int
   OMLM_CHECK_ARG(R > 0 && C > 0, "split3: empty");
   const long total = static_cast<long>(R) * C;
   const int blocks = static_cast<int>(std::min<long>((total + 255) / 256, 2048));
-  split3_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, src_ld, reinterpret_cast<__nv_bfloat16*>(dst), R, C, weight_mode);
+  OMLM_KLAUNCH((split3_kernel), blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream), src, src_ld, reinterpret_cast<__nv_bfloat16*>(dst), R, C, weight_mode);
   OMLM_LAUNCH_CHECK();
   return 0;
 }
@@ -190,7 +196,7 @@ int omlm_bias_silu(float* z, const float* bias, float* a, int R, int C, void* st
   OMLM_CHECK_ARG(R > 0 && C > 0, "bias_silu: empty");
   const long total = static_cast<long>(R) * C;
   const int blocks = static_cast<int>(std::min<long>((total + 255) / 256, 2048));
-  bias_silu_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(z, bias, a, R, C);
+  OMLM_KLAUNCH((bias_silu_kernel), blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream), z, bias, a, R, C);
   OMLM_LAUNCH_CHECK();
   return 0;
 }
@@ -198,7 +204,7 @@ int omlm_bias_silu(float* z, const float* bias, float* a, int R, int C, void* st
 int omlm_arange_f32(float* out, int n, void* stream) {
   using namespace omlm;
   OMLM_CHECK_ARG(n > 0, "arange: empty");
-  arange_kernel<<<(n + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out, n);
+  OMLM_KLAUNCH((arange_kernel), (n + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream), out, n);
   OMLM_LAUNCH_CHECK();
   return 0;
 }

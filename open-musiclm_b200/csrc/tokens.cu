@@ -29,6 +29,7 @@ __global__ void token_plan_kernel(const TokenPlanArgs a, const unsigned char* __
                                   long long* __restrict__ ids_out, int* __restrict__ src_row,
                                   unsigned char* __restrict__ key_mask, int* __restrict__ labels,
                                   int* __restrict__ err_flag, int N, int n_ids_total, int n_labels_total) {
+  pdl_prologue();
   const int b = blockIdx.x;
   int pos = 0, id_off = 0, lab_off = 0;
   for (int s = 0; s < a.n_seqs; ++s) {
@@ -84,6 +85,7 @@ __global__ void token_plan_kernel(const TokenPlanArgs a, const unsigned char* __
 __global__ void forgetful_mask_kernel(unsigned char* __restrict__ keep, int N, int num_drop,
                                       const unsigned long long* __restrict__ seed_ptr,
                                       unsigned long long stream_id) {
+  pdl_prologue();
   extern __shared__ unsigned int keys[];
   const int b = blockIdx.x;
   const unsigned long long seed = *seed_ptr;
@@ -109,6 +111,7 @@ __global__ void forgetful_mask_kernel(unsigned char* __restrict__ keep, int N, i
 // a negative row contributes zero.  fp32 table, fp32 out; 128-bit copies.
 __global__ void embed_gather_kernel(const float* __restrict__ table, const int* __restrict__ src_row,
                                     const int* __restrict__ src_row2, float* __restrict__ x, int M, int D) {
+  pdl_prologue();
   const int vec_per_row = D >> 2;
   const long long total = static_cast<long long>(M) * vec_per_row;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -131,6 +134,7 @@ __global__ void embed_gather_kernel(const float* __restrict__ table, const int* 
 // dtable[src_row[m], :] += scale * dx[m, :]   (scale = grad_shrink alpha, utils.py:60-61).
 __global__ void embed_scatter_kernel(float* __restrict__ dtable, const int* __restrict__ src_row,
                                      const float* __restrict__ dx, int M, int D, float scale) {
+  pdl_prologue();
   const int vec_per_row = D >> 2;
   const long long total = static_cast<long long>(M) * vec_per_row;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -172,7 +176,7 @@ int omlm_token_plan(int n_seqs, const long long* const* ids, const int* len, con
     OMLM_CHECK_ARG(n_tok >= 0, "token_plan: sequence %d too short", s);
     N += 1 + n_tok; n_ids += n_tok; n_lab += n_with_eos;
   }
-  token_plan_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  OMLM_KLAUNCH((token_plan_kernel), B, 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       a, mask_in, forget_keep, ids_out, src_row, key_mask, labels, err_flag, N, n_ids, n_lab);
   OMLM_LAUNCH_CHECK();
   return 0;
@@ -183,7 +187,7 @@ int omlm_forgetful_mask(unsigned char* keep, int B, int N, int num_drop,
   using namespace omlm;
   OMLM_CHECK_ARG(B > 0 && N > 0 && N <= 12000, "forgetful_mask: bad shape %d x %d", B, N);
   OMLM_CHECK_ARG(num_drop >= 0 && num_drop < N, "forgetful_mask: num_drop %d out of range", num_drop);
-  forgetful_mask_kernel<<<B, 512, N * sizeof(unsigned int), reinterpret_cast<cudaStream_t>(stream)>>>(
+  OMLM_KLAUNCH((forgetful_mask_kernel), B, 512, N * sizeof(unsigned int), reinterpret_cast<cudaStream_t>(stream), 
       keep, N, num_drop, seed, stream_id);
   OMLM_LAUNCH_CHECK();
   return 0;
@@ -194,7 +198,7 @@ int omlm_embed_gather(const float* table, const int* src_row, const int* src_row
   OMLM_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0, "embed_gather: bad shape %d x %d", M, D);
   const long long total = static_cast<long long>(M) * (D / 4);
   const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(num_sms()) * 16));
-  embed_gather_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(table, src_row, src_row2, x, M, D);
+  OMLM_KLAUNCH((embed_gather_kernel), grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), table, src_row, src_row2, x, M, D);
   OMLM_LAUNCH_CHECK();
   return 0;
 }
@@ -205,7 +209,7 @@ int omlm_embed_scatter_add(float* dtable, const int* src_row, const float* dx, i
   OMLM_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0, "embed_scatter: bad shape %d x %d", M, D);
   const long long total = static_cast<long long>(M) * (D / 4);
   const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(num_sms()) * 16));
-  embed_scatter_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dtable, src_row, dx, M, D, scale);
+  OMLM_KLAUNCH((embed_scatter_kernel), grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), dtable, src_row, dx, M, D, scale);
   OMLM_LAUNCH_CHECK();
   return 0;
 }
@@ -219,6 +223,7 @@ int omlm_embed_scatter_add(float* dtable, const int* src_row, const float* dx, i
 namespace omlm {
 __global__ void gather_windows_kernel(const short* __restrict__ src, const long long* __restrict__ start, long long* __restrict__ out,
                                       int len, int width, int B) {
+  pdl_prologue();
   const long long per_row = static_cast<long long>(len) * width;
   const long long total = per_row * B;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -235,7 +240,7 @@ extern "C" int omlm_gather_windows(const void* src_i16, const long long* start, 
   if (len == 0) return 0;
   const long long total = static_cast<long long>(len) * width * B;
   const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(num_sms()) * 8));
-  gather_windows_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const short*>(src_i16), start, out, len, width, B);
+  OMLM_KLAUNCH((gather_windows_kernel), grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const short*>(src_i16), start, out, len, width, B);
   OMLM_LAUNCH_CHECK();
   return 0;
 }

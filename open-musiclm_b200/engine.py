@@ -431,7 +431,10 @@ class Engine:
         x = ws["x"]
         drop_p = self.drop_p if drop else 0.0
         # ---- logit heads
-        ws["dxf"].zero_()
+        gset = frozenset(groups_with_grad)
+        if ws.get("dxf_groups") != gset:      # rows of head groups without a gradient stay zero; the others are overwritten
+            ws["dxf"].zero_()
+            ws["dxf_groups"] = gset
         for gi, (s, qi, cnt, base) in enumerate(pl.groups):
             if s not in groups_with_grad:
                 continue
@@ -451,7 +454,6 @@ class Engine:
             lib.gemm(ws["dx_bf"], pk["w2_b"], ws["dhn"], b_mn=True, M=M, N=Fp, K=d, block_n=self._bn_for(M, Fp, d), max_ctas=self.bwd_max_ctas)
             fk = self.ffk
             self._wgrad(ws["dx_bf"], ws["hn"][l], gv[p + fk["w2"]], d, Fp, n_valid=F)
-            ws["dgin"].zero_(); ws["dconv"].zero_()
             lib.ffn_mid_bwd(ws["dhn"], ws["hn"][l], ws["u"][l], ws["st_i"][l], pk["conv"], pk["gin"], ws["rowstat"], ws["du"],
                             ws["dgin"], ws["dconv"], B, N, F, Fp, drop_p, keep_bits=ws["keep"][l] if drop_p > 0 else None)
             lib.unpack_add(ws["dgin"], 1, Fp, gv[p + fk["gin"]], F, 1, F)
@@ -463,7 +465,6 @@ class Engine:
             # ---- attention
             lib.gemm(ws["dx_bf"], pk["wo_b"], ws["d_o"], b_mn=True, M=M, N=HD, K=d, block_n=self._bn_for(M, HD, d), max_ctas=self.bwd_max_ctas)
             self._wgrad(ws["dx_bf"], ws["o"][l], gv[p + "0.to_out.0.weight"], d, HD)
-            ws["dqn"].zero_(); ws["dkvn"].zero_()
             lib.attn_bwd_tc(ws["qn"][l], ws["kvn"][l], ws["d_o"], ws["o"][l], ws["lse"][l], ws["table"], key_mask, ws["dsum"],
                             ws["dqn"], ws["dkvn"], ws["dtable"], B, N, h)
             lib.qk_l2norm_bwd(ws["dqn"], ws["dkvn"], ws["q_raw"][l], ws["kv_raw"][l], pv[p + "0.q_scale"], pv[p + "0.k_scale"],

@@ -230,7 +230,8 @@ def test_attention_fwd_bwd(lib, B, N, h):
     assert rel(dkvn, kvf.grad) < 1.5e-2
     assert rel(dtab[:, :N], tf.grad[:, :N]) < 1.5e-2
     # tcgen05 backward
-    dqn2 = torch.zeros(M, h * 64, device=DEV); dkvn2 = torch.zeros(M, 128, device=DEV); dtab2 = torch.zeros_like(table)
+    # dqn / dkvn are overwritten (cleared inside the call): poison them to pin that contract; dtable accumulates
+    dqn2 = torch.full((M, h * 64), float("nan"), device=DEV); dkvn2 = torch.full((M, 128), float("nan"), device=DEV); dtab2 = torch.zeros_like(table)
     lib.attn_bwd_tc(qn, kvn, d_o, out, lse2, table, key_mask, dsum, dqn2, dkvn2, dtab2, B, N, h)
     torch.cuda.synchronize()
     assert rel(dqn2, qf.grad) < 1.5e-2, rel(dqn2, qf.grad)
@@ -306,7 +307,7 @@ def test_ffn_up_fused_and_mid_bwd(lib, B, N, d, F_, drop_p, adt):
     dhn[:, :F_] = torch.randn(M, F_, device=DEV).bfloat16()
     ref.backward(dhn[:, :F_].float())
     du = torch.empty(M, 2 * Fp, device=DEV, dtype=torch.bfloat16); rowstat = torch.empty(M, 2, device=DEV)
-    dg = torch.zeros(Fp, device=DEV); dcw = torch.zeros(2 * Fp, 3, device=DEV)
+    dg = torch.full((Fp,), float("nan"), device=DEV); dcw = torch.full((2 * Fp, 3), float("nan"), device=DEV)   # overwritten by the call
     lib.ffn_mid_bwd(dhn, hn_b, u, stats, cwp, gp, rowstat, du, dg, dcw, B, N, F_, Fp, drop_p, keep_bits=kbits if drop_p > 0 else None)
     assert rel(du[:, cols], uf.grad) < 1.5e-2
     assert rel(dg[:F_], gr.grad) < 8e-3

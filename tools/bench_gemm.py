@@ -20,7 +20,10 @@ shapes = [("q", "fwd", M, HD, d), ("kv", "fwd", M, 128, d), ("out", "fwd_res", M
           ("d_hn", "dgrad", M, Fp, d), ("d_xn2", "dgrad", M, d, 2 * Fp), ("d_o", "dgrad", M, HD, d), ("d_xn(q)", "dgrad", M, d, HD), ("d_xraw", "dgrad", M, d, 128),
           ("dW2", "wgrad", d, Fp, M), ("dW1", "wgrad", 2 * Fp, d, M), ("dWo", "wgrad", d, HD, M), ("dWq", "wgrad", HD, d, M), ("dWkv", "wgrad", 128, d, M)]
 total = {}
+kinds = os.environ.get("BENCH_GEMM_KINDS", "fwd,fwd_res,dgrad,wgrad").split(",")
 for name, kind, m, n, k in shapes:
+    if kind not in kinds:
+        continue
     fl = 2.0 * m * n * k
     if kind in ("fwd", "fwd_res"):
         a, b = bf(m, k), bf(n, k)

@@ -20,18 +20,21 @@ from open_musiclm_b200 import lib  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ncu", action="store_true")
-    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--config", default="cfg2")
     ap.add_argument("--depth", type=int, default=None, help="override the layer count (1 keeps an ncu --set full capture short)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "step_breakdown.json"))
     args = ap.parse_args()
     torch.manual_seed(0)
-    cfg = dict(bench.CFG)
+    wl = bench.WORKLOADS[args.config]
+    cfg = dict(bench.COMMON, **wl["model"])
     if args.depth is not None:
         cfg["depth"] = args.depth
-    model = O.create_coarse_transformer(**cfg).cuda()
+    fn = {"coarse": O.create_coarse_transformer, "fine": O.create_fine_transformer}[wl["stage"]]
+    model = fn(**cfg).cuda()
     tr = O.HotPathTrainer(model, cross_entropy_loss_weights=bench.TRAIN["ce_weights"], lr=3e-4, lr_warmup=6000, wd=0.01, use_cuda_graph=False)
     gen = torch.Generator().manual_seed(1234)
-    batch = [t.cuda() for t in bench.synth_batch(args.batch, gen)]
+    batch = [t.cuda() for t in bench.synth_batch(args.batch or wl["batch"], gen, wl["shapes"])]
     for _ in range(3):
         tr.train_step([batch])
     torch.cuda.synchronize()

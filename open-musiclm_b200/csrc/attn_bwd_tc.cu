@@ -64,15 +64,21 @@ __device__ __forceinline__ uint32_t bt_tile_off(int row, int ch) {
 // Diagonal sums of one dS tile, fast path for h = 128 / IPT heads (tile rows = IPT positions x h heads).
 // A thread owns (head hh, 8-key chunk ch) and walks the tile's IPT positions; element (il, key c) belongs to the
 // diagonal i - j = const, i.e. to register bin il - (c % 8) + 7: all indices are static after unrolling.
+// Two steps so that the dS tiles are released before the shared table is touched:
+//   bt_diag_gather: tile -> register bins (NU = 16 H / 128 units per thread);
+//   bt_diag_flush : register bins -> per-CTA table.  The strips of chunks ch and ch + 3 of one head do not overlap
+//                   (23 bins, 8 apart), so three rounds of plain read-modify-write separated by the warpgroup's named
+//                   barrier replace the shared-memory float atomics (CAS loops in SASS).
 template <int IPT>
-__device__ __forceinline__ void bt_diag_fast(const uint8_t* ds_hi, const uint8_t* ds_lo, float* dacc, int Wacc, int tid,
-                                             int base_t) {
-  constexpr int H = 128 / IPT;
-  for (int u = tid; u < 16 * H; u += 128) {
-    const int hh = u % H, ch = u / H;
-    float acc[IPT + 7];
+__device__ __forceinline__ void bt_diag_gather(const uint8_t* ds_hi, const uint8_t* ds_lo, int tid,
+                                               float (&acc)[16 * (128 / IPT) / 128][IPT + 7]) {
+  constexpr int H = 128 / IPT, NU = 16 * H / 128;
 #pragma unroll
-    for (int k = 0; k < IPT + 7; ++k) acc[k] = 0.f;
+  for (int n = 0; n < NU; ++n) {
+    const int u = tid + n * 128;
+    const int hh = u % H, ch = u / H;
+#pragma unroll
+    for (int k = 0; k < IPT + 7; ++k) acc[n][k] = 0.f;
 #pragma unroll
     for (int il = 0; il < IPT; ++il) {
       const uint32_t off = bt_tile_off(il * H + hh, ch);
@@ -82,14 +88,29 @@ __device__ __forceinline__ void bt_diag_fast(const uint8_t* ds_hi, const uint8_t
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float2 x = unpack_bf16x2(aw[q]), y = unpack_bf16x2(bw[q]);
-        acc[il - 2 * q + 7] += x.x + y.x;       // key 8 ch + 2q
-        acc[il - 2 * q + 6] += x.y + y.y;       // key 8 ch + 2q + 1
+        acc[n][il - 2 * q + 7] += x.x + y.x;       // key 8 ch + 2q
+        acc[n][il - 2 * q + 6] += x.y + y.y;       // key 8 ch + 2q + 1
       }
     }
-    float* dst = dacc + hh * Wacc + base_t + 120 - ch * 8;
+  }
+}
+template <int IPT>
+__device__ __forceinline__ void bt_diag_flush(float* dacc, int Wacc, int tid, int base_t,
+                                              const float (&acc)[16 * (128 / IPT) / 128][IPT + 7]) {
+  constexpr int H = 128 / IPT, NU = 16 * H / 128;
 #pragma unroll
-    for (int k = 0; k < IPT + 7; ++k)
-      if (acc[k] != 0.f) atomicAdd(dst + k, acc[k]);
+  for (int phase = 0; phase < 3; ++phase) {
+#pragma unroll
+    for (int n = 0; n < NU; ++n) {
+      const int u = tid + n * 128;
+      const int hh = u % H, ch = u / H;
+      if (ch % 3 == phase) {
+        float* dst = dacc + hh * Wacc + base_t + 120 - ch * 8;
+#pragma unroll
+        for (int k = 0; k < IPT + 7; ++k) dst[k] += acc[n][k];
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
   }
 }
 
@@ -301,6 +322,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int sw = row_local & 7;
     const float sc2 = scale * kBtL2e;
     const float* kn = kneg + half * 64;
+    // per-row softmax statistics: loaded one tile ahead (a dependent global load at the top of every tile stalled the warp)
+    auto row_stats = [&](int t, float& l2v, float& dsmv) {
+      const int rr = (rt_begin + t) * kBtBQ + row_local;
+      const bool ok = t < T && rr < R;
+      l2v = ok ? __ldg(lse2 + static_cast<long long>(b) * R + rr) : INFINITY;
+      dsmv = ok ? __ldg(dsum + static_cast<long long>(b) * R + rr) : 0.f;
+    };
+    float l2_nx, dsm_nx;
+    row_stats(0, l2_nx, dsm_nx);
     for (int t = 0; t < T; ++t) {
       const int buf = t & 1;
       const int r0 = (rt_begin + t) * kBtBQ;
@@ -308,8 +338,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int rc = min(r, R - 1);
       const int i = rc / h, hh = rc - i * h;
       const int i_min = r0 / h;
-      const float l2 = (r < R) ? lse2[static_cast<long long>(b) * R + r] : INFINITY;
-      const float dsm = (r < R) ? dsum[static_cast<long long>(b) * R + r] : 0.f;
+      const float l2 = l2_nx, dsm = dsm_nx;
+      row_stats(t + 1, l2_nx, dsm_nx);
       mbar_wait(&b_full[buf], (t >> 1) & 1);
       mbar_wait(sd_full, t & 1);
       tc_fence_after();
@@ -371,11 +401,23 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     for (int t = 0; t < T; ++t) {
       const int r0 = (rt_begin + t) * kBtBQ;
       mbar_wait(pds_full, t & 1);
-      if (h == 8) bt_diag_fast<16>(smem + kBoDS, smem + kBoDSL, dacc, Wacc, tid, r0 / h - i_min0);
-      else if (h == 16) bt_diag_fast<8>(smem + kBoDS, smem + kBoDSL, dacc, Wacc, tid, r0 / h - i_min0);
-      else bt_diag_generic(smem + kBoDS, smem + kBoDSL, dacc, Wacc, tid, r0, R, h, i_min0);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(diag_free);
+      if (h == 8) {
+        float acc[1][23];
+        bt_diag_gather<16>(smem + kBoDS, smem + kBoDSL, tid, acc);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(diag_free);          // the dS tiles are free again before the table is updated
+        bt_diag_flush<16>(dacc, Wacc, tid, r0 / h - i_min0, acc);
+      } else if (h == 16) {
+        float acc[2][15];
+        bt_diag_gather<8>(smem + kBoDS, smem + kBoDSL, tid, acc);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(diag_free);
+        bt_diag_flush<8>(dacc, Wacc, tid, r0 / h - i_min0, acc);
+      } else {
+        bt_diag_generic(smem + kBoDS, smem + kBoDSL, dacc, Wacc, tid, r0, R, h, i_min0);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(diag_free);
+      }
       // ---- dQ of this tile
       const int r = r0 + row_local;
       mbar_wait(dq_full, t & 1);

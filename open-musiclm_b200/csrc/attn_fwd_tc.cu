@@ -49,6 +49,16 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* r) {
       : "r"(taddr));
 }
 
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* r) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(r);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+        "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+      : "r"(taddr));
+}
+
 __device__ __forceinline__ float ex2_fast(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -108,7 +118,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   pdl_wait();   // private set-up done: from here on global memory written by the previous kernel is touched
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
       // ------------------------------------------------------------------ TMA producer
       if (lane == 0) {
@@ -182,12 +192,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const int i_min = (r0 + wg * kTcBQ) / h;
           const int delta_min = i_min - j0 - (kTcBK - 1);
           float* dst = bias + (buf * 2 + wg) * slice;
-          // all loads of 8 head rows are issued back to back (32 independent L2/L1 requests per thread) before
+          // all loads of 4 head rows are issued back to back (16 independent L2/L1 requests per thread) before
           // any store: the slice build must stay well below one tile of softmax time
-          for (int hh0 = 0; hh0 < h; hh0 += 8) {
-            float v[8][4];
+          for (int hh0 = 0; hh0 < h; hh0 += 4) {
+            float v[4][4];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < 4; ++k) {
               const int hh = min(hh0 + k, h - 1);
               const float* trow = table + hh * table_ld;
 #pragma unroll
@@ -198,7 +208,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               }
             }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < 4; ++k) {
               if (hh0 + k < h) {
                 float* drow = dst + (hh0 + k) * W;
 #pragma unroll
@@ -221,7 +231,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else {
     // -------------------------------------------------------------------- softmax warpgroups
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     const int wg = (warp - 4) >> 2;
     const int quarter = warp & 3;
     const int row_local = quarter * 32 + lane;
@@ -272,34 +282,35 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const float ref = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = ex2_fast(m - ref);
       m = m_new;
-      float sum = 0.f;
-      uint32_t pk[64];
-#pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        const float p0 = ex2_fast(s[2 * c] - ref), p1 = ex2_fast(s[2 * c + 1] - ref);
-        sum += p0 + p1;
-        pk[c] = pack_bf16x2(p0, p1);
-      }
-      l = l * alpha + sum;
-      // ---- O_tile of the PREVIOUS tile (its PV MMA ran while this tile's softmax was computed)
+      // ---- O_tile of the PREVIOUS tile first (its PV MMA was issued a whole tile ago): once o_full(t-1) has been
+      //      observed the P buffer is free as well, so the exponentials below stream straight into shared memory
+      //      instead of being parked in 64 registers
       if (t > 0) {
         mbar_wait(&o_full[wg], (t - 1) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          float ot[32];
-          tmem_ld32_nowait(t_o + hf * 32, ot);
+        for (int qd = 0; qd < 4; ++qd) {     // 16 columns at a time: the S row (128 registers) is still live here
+          float ot[16];
+          tmem_ld16_nowait(t_o + qd * 16, ot);
           tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 32; ++c) o_acc[hf * 32 + c] = fmaf(o_acc[hf * 32 + c], alpha_prev, ot[c]);
+          for (int c = 0; c < 16; ++c) o_acc[qd * 16 + c] = fmaf(o_acc[qd * 16 + c], alpha_prev, ot[c]);
         }
       }
       alpha_prev = alpha;
-      // ---- P -> smem (the previous PV has finished reading this buffer: o_full(t-1) was observed above)
+      // ---- P = exp2(s - ref) -> bf16 -> smem; four independent partial sums (one serial FADD chain stalled on every MUFU)
+      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
 #pragma unroll
-      for (int ch = 0; ch < 16; ++ch)
+      for (int ch = 0; ch < 16; ++ch) {
+        const float p0 = ex2_fast(s[8 * ch + 0] - ref), p1 = ex2_fast(s[8 * ch + 1] - ref);
+        const float p2 = ex2_fast(s[8 * ch + 2] - ref), p3 = ex2_fast(s[8 * ch + 3] - ref);
+        const float p4 = ex2_fast(s[8 * ch + 4] - ref), p5 = ex2_fast(s[8 * ch + 5] - ref);
+        const float p6 = ex2_fast(s[8 * ch + 6] - ref), p7 = ex2_fast(s[8 * ch + 7] - ref);
+        sum0 += p0 + p1; sum1 += p2 + p3; sum2 += p4 + p5; sum3 += p6 + p7;
         *reinterpret_cast<uint4*>(prow + (ch >> 3) * 16384 + (((ch & 7) ^ sw) << 4)) =
-            make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+            make_uint4(pack_bf16x2(p0, p1), pack_bf16x2(p2, p3), pack_bf16x2(p4, p5), pack_bf16x2(p6, p7));
+      }
+      l = l * alpha + ((sum0 + sum1) + (sum2 + sum3));
       fence_proxy_async();       // P (generic-proxy stores) must be visible to the tensor core's async proxy
       tc_fence_before();         // orders this thread's TMEM reads (S, O) before the MMA warp overwrites them
       __syncwarp();

@@ -50,6 +50,16 @@ int omlm_gemm16(const void* A, int a_f16, int a_mn_major, long lda, const void* 
                 long ldadd, float alpha, int splits, int row_split, int row_valid, int n_valid,
                 int block_n, int max_ctas, void* stream);
 
+/* The same GEMM (dense bf16 output [M, N], 256-wide tiles, N % 256 == 0) whose epilogue also leaves, per output row and
+ * 128-column half tile, the two row sums LayerNorm-backward needs against a saved tensor hn bf16 [M, N]:
+ *   part[m, j, 0] = keep_scale * sum_{c in half tile j} gamma[c] * (keep_bit(m, c) ? d[m, c] : 0),
+ *   part[m, j, 1] = sum_{c in half tile j} d[m, c] * hn[m, c],      j < parts = N / 128  (d = this GEMM's fp32 result).
+ * Used for the d_hn data gradient of the conv feed-forward (transformer.py:140-150 backward): replaces a separate pass
+ * over (dhn, hn).  keep_bits uint8 [M, N/8] or NULL. */
+int omlm_gemm16_rowstat(const void* A, int a_f16, int a_mn_major, long lda, const void* B, int b_f16, int b_mn_major, long ldb,
+                        int M, int N, int K, void* out_bf16, long ldo, const void* hn_bf16, long ldhn, const void* keep_bits,
+                        const float* gamma, float keep_scale, float* part, int parts, int max_ctas, void* stream);
+
 /* ---- integer token path (bit-exact) ------------------------------------------------------------
  * One pass over the raw ids of all sequences of a TokenConditionedTransformer batch.
  * Wrapper mode (append_eos=1): eos (= codebook size) appended to every sequence
@@ -153,11 +163,14 @@ int omlm_gemm_ffn_up(const void* xn, const void* w1_packed, const float* conv_w_
 int omlm_ffn_norm_fwd(const void* h, const float* rowsum, const float* gamma, void* hn, void* hn_copy_bf16, float* stats,
                       void* keep_bits, long M, int F, int Fp, float drop_p, const unsigned long long* seed, int layer,
                       int act_f16, void* stream);
-/* dhn, hn (saved forward output), keep_bits (from omlm_ffn_norm_fwd; may be NULL when drop_p == 0) ->
- * du bf16 [B*N, 2Fp]; dgamma [Fp] and dconv_w [2Fp,3] are OVERWRITTEN (cleared by the statistics kernel, reduced into
- * by the tile kernel); rowstat_scratch fp32 [B*N, 2]. */
+/* dhn, hn (saved forward output), keep_bits (from omlm_ffn_norm_fwd; may be NULL when drop_p == 0) -> du bf16 [B*N, 2Fp].
+ * Parameter gradients are ACCUMULATED (+=) in the parameters' own layouts: dgamma [F] (inner LayerNorm gamma) and
+ * dconv_w [2F, 3] (ds_conv.weight: value rows [0,F), gate rows [F,2F); may be NULL for the plain FeedForward).
+ * rowstat: the LayerNorm-backward row sums (sum gamma*drop(dhn), sum dhn*hn) as fp32 [B*N, parts, 2]:
+ *   rowstat_parts > 0: partial sums written by omlm_gemm16_rowstat (the d_hn GEMM's epilogue), parts = Fp / 128;
+ *   rowstat_parts = 0: rowstat is a [B*N, 2] scratch and the sums are computed here by one extra pass over (dhn, hn). */
 int omlm_ffn_mid_bwd(const void* dhn, const void* hn, const void* u, const float* stats, const float* conv_w,
-                     const float* gamma, const void* keep_bits, float* rowstat_scratch, void* du, float* dgamma,
+                     const float* gamma, const void* keep_bits, float* rowstat, int rowstat_parts, void* du, float* dgamma,
                      float* dconv_w, int B, int N, int F, int Fp, float drop_p, int act_f16, void* stream);
 
 /* ---- cross entropy (open_musiclm.py:401) --------------------------------------------------------

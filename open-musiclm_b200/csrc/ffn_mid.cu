@@ -128,14 +128,9 @@ ffn_norm_fwd_kernel(const __nv_bfloat16* __restrict__ h, const float2* __restric
 __global__ void __launch_bounds__(256)
 ffn_mid_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dhn, const __nv_bfloat16* __restrict__ hn,
                          const float* __restrict__ gamma, float2* __restrict__ rowstat, long M, int F, int Fp,
-                         float drop_p, const uint8_t* __restrict__ keep_bits, float* __restrict__ dgamma,
-                         float* __restrict__ dconv_w) {
+                         float drop_p, const uint8_t* __restrict__ keep_bits) {
   pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // the walk kernel reduces its parameter gradients into dgamma [Fp] and dconv_w [2 Fp, 3]: cleared here
-  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < 7L * Fp; i += static_cast<long>(gridDim.x) * blockDim.x) {
-    if (i < Fp) dgamma[i] = 0.f; else dconv_w[i - Fp] = 0.f;
-  }
   const long row = static_cast<long>(blockIdx.x) * 8 + warp;
   if (row >= M) return;
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
@@ -156,7 +151,7 @@ ffn_mid_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dhn, const __nv_bfloa
     }
   }
   s1 = warp_sum(s1); s2 = warp_sum(s2);
-  if (lane == 0) rowstat[row] = make_float2(s1 / F, s2 / F);
+  if (lane == 0) rowstat[row] = make_float2(s1, s2);     // raw sums (one "partial"); the tile kernel divides by F
 }
 
 // Tile geometry of the walk: a CTA owns 128 time steps x one 128-channel group (= 256 contiguous u columns in the
@@ -187,7 +182,7 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool
 template <bool F16>
 __global__ void __launch_bounds__(kTileThreads, 2)
 ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, const float2* __restrict__ stats,
-                        const float2* __restrict__ rowstat, __nv_bfloat16* __restrict__ du,
+                        const float2* __restrict__ rowstat, const int parts, __nv_bfloat16* __restrict__ du,
                         float* __restrict__ dgamma, float* __restrict__ dconv_w) {
   pdl_prologue();
   extern __shared__ __align__(16) uint8_t tsm[];
@@ -220,11 +215,26 @@ ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, 
     const bool ok = t < a.N;
     const long long row = row_base + (ok ? t : 0);
     cp_async8(reinterpret_cast<uint8_t*>(sst + tid), stats + row, ok);
-    cp_async8(reinterpret_cast<uint8_t*>(sst + tid) + 8, rowstat + row, ok);
     if (a.drop_p > 0.f) cp_async16(skb + tid * 16, a.keep_bits + row * (a.Fp >> 3) + g * 16, ok);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
   for (int i = tid; i < 7 * 128; i += kTileThreads) sacc[i] = 0.f;
+  // LayerNorm-backward row means m1, m2: `parts` partial sums per row (from the d_hn GEMM's epilogue, or one from the
+  // statistics kernel), added in a fixed order.  Plain loads into the .zw half of the row constants (the cp.async above
+  // writes only .xy of the same float4)
+  if (tid < kTdRows) {       // one thread per row; the (<= 32) partial sums are loaded back to back, then added in order
+    const int t = tb + tid;
+    float2 v[32];
+    const float2* pr = rowstat + (row_base + min(t, a.N - 1)) * parts;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = (k < parts) ? __ldg(pr + k) : make_float2(0.f, 0.f);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) { s1 += v[k].x; s2 += v[k].y; }
+    for (int k = 32; k < parts; ++k) { const float2 w = __ldg(pr + k); s1 += w.x; s2 += w.y; }
+    const float invF = 1.f / a.F;
+    reinterpret_cast<float2*>(sst + tid)[1] = (t < a.N) ? make_float2(s1 * invF, s2 * invF) : make_float2(0.f, 0.f);
+  }
 
   // ---- per-lane constants: 4 value + 4 gate channels, held as two fp32x2 pairs (channels 2q, 2q+1)
   const int c0 = g * 128 + lane * 4;                   // natural channel index of this lane's first channel
@@ -344,12 +354,17 @@ ffn_mid_bwd_walk_kernel(const MidArgs a, const __nv_bfloat16* __restrict__ dhn, 
     }
   }
   __syncthreads();
+  // parameter gradients in the parameters' own layout: inner gamma [F]; conv taps [2F, 3] with the value half in rows
+  // [0, F) and the gate half in rows [F, 2F) (transformer.py:122-137) -- accumulated (+=), padded channels dropped
   for (int i = tid; i < 7 * 128; i += kTileThreads) {
-    const int q = i >> 7, c = i & 127;
+    const int q = i >> 7, ch = g * 128 + (i & 127);
+    if (ch >= a.F) continue;
     const float v = sacc[i];
-    if (q == 0) atomicAdd(&dgamma[g * 128 + c], v);
-    else if (q < 4) atomicAdd(&dconv_w[(g * 256 + c) * 3 + (q - 1)], v);
-    else atomicAdd(&dconv_w[(g * 256 + 128 + c) * 3 + (q - 4)], v);
+    if (q == 0) atomicAdd(&dgamma[ch], v);
+    else if (dconv_w != nullptr) {
+      if (q < 4) atomicAdd(&dconv_w[static_cast<long>(ch) * 3 + (q - 1)], v);
+      else atomicAdd(&dconv_w[(static_cast<long>(a.F) + ch) * 3 + (q - 4)], v);
+    }
   }
 }
 
@@ -375,7 +390,7 @@ int omlm_ffn_norm_fwd(const void* h, const float* rowsum, const float* gamma, vo
 }
 
 int omlm_ffn_mid_bwd(const void* dhn, const void* hn, const void* u, const float* stats, const float* conv_w,
-                     const float* gamma, const void* keep_bits, float* rowstat_scratch, void* du, float* dgamma,
+                     const float* gamma, const void* keep_bits, float* rowstat, int rowstat_parts, void* du, float* dgamma,
                      float* dconv_w, int B, int N, int F, int Fp, float drop_p, int act_f16, void* stream) {
   using namespace omlm;
   OMLM_CHECK_ARG(B > 0 && N > 0 && F > 0 && Fp >= F && Fp % 128 == 0, "ffn_mid_bwd: bad shape F=%d Fp=%d", F, Fp);
@@ -385,10 +400,14 @@ int omlm_ffn_mid_bwd(const void* dhn, const void* hn, const void* u, const float
   const long M = static_cast<long>(B) * N;
   auto stats_kern = ffn_mid_bwd_stats_kernel;
   auto walk_kern = act_f16 ? ffn_mid_bwd_walk_kernel<true> : ffn_mid_bwd_walk_kernel<false>;
-  OMLM_KLAUNCH((stats_kern), static_cast<int>((M + 7) / 8), 256, 0, st, 
-      reinterpret_cast<const __nv_bfloat16*>(dhn), reinterpret_cast<const __nv_bfloat16*>(hn), gamma,
-      reinterpret_cast<float2*>(rowstat_scratch), M, F, Fp, drop_p, a.keep_bits, dgamma, dconv_w);
-  OMLM_LAUNCH_CHECK();
+  OMLM_CHECK_ARG(rowstat_parts >= 0 && rowstat != nullptr, "ffn_mid_bwd: rowstat buffer / parts");
+  if (rowstat_parts == 0) {      // no partial sums from the d_hn GEMM: one pass over (dhn, hn) here
+    OMLM_KLAUNCH((stats_kern), static_cast<int>((M + 7) / 8), 256, 0, st,
+        reinterpret_cast<const __nv_bfloat16*>(dhn), reinterpret_cast<const __nv_bfloat16*>(hn), gamma,
+        reinterpret_cast<float2*>(rowstat), M, F, Fp, drop_p, a.keep_bits);
+    OMLM_LAUNCH_CHECK();
+    rowstat_parts = 1;
+  }
   static bool configured = false;
   if (!configured) {
     OMLM_CUDA(cudaFuncSetAttribute(ffn_mid_bwd_walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem));
@@ -398,7 +417,7 @@ int omlm_ffn_mid_bwd(const void* dhn, const void* hn, const void* u, const float
   dim3 grid(B * ((N + kTileRows - 1) / kTileRows), Fp / 128);
   OMLM_KLAUNCH((walk_kern), grid, kTileThreads, kTileSmem, st, a, reinterpret_cast<const __nv_bfloat16*>(dhn),
                                                                 reinterpret_cast<const float2*>(stats),
-                                                                reinterpret_cast<const float2*>(rowstat_scratch),
+                                                                reinterpret_cast<const float2*>(rowstat), rowstat_parts,
                                                                 reinterpret_cast<__nv_bfloat16*>(du), dgamma, dconv_w);
   OMLM_LAUNCH_CHECK();
   return 0;

@@ -40,12 +40,24 @@ struct EpiParams {
   int row_split;  // >0: rows are two halves of row_split, each with row_valid live rows; <0: interleaved GEGLU groups of 128
   int row_valid;
   int n_valid;    // columns >= n_valid are dropped
-  int tma_mode;   // 0: per-thread global stores; 1: TMA store; 2: TMA addend in place + TMA store; 3: TMA addend prefetched (2 buffers) + TMA store
+  int tma_mode;   // 0: per-thread global stores; 1: TMA store; 2: TMA addend in place + TMA store; 3: TMA addend prefetched (2 buffers) + TMA store;
+                  // 4: TMA store + row statistics against a second [M, N] bf16 tensor (below)
+  // mode 4 (the d_hn data-gradient GEMM of the conv feed-forward): with d = this GEMM's fp32 output row and hn the saved
+  // forward output, every epilogue warp leaves  part[row, 2 n_blk + half] = (sum_c gamma[c] drop(d[c]), sum_c d[c] hn[c])
+  // over its half tile -- the two row sums LayerNorm-backward needs (ffn_mid.cu), which used to cost a separate pass
+  // hn arrives through tmAdd (bf16 boxes of 64 columns x 32 rows) into one staging buffer per warp, one chunk ahead
+  const float* rs_gamma;       // [N] fp32 (zero in padded columns)
+  const uint8_t* rs_keep;      // dropout keep bits [M, N/8] or nullptr
+  float2* rs_part;             // [M, rs_parts]
+  float rs_keep_scale;         // 1 / (1 - p)
+  int rs_parts;
 };
 
 constexpr int kEpiWarps = 8;
 constexpr int kEpiBuf = 4096;     // one staging buffer: 32 rows x 128 bytes, 128B-swizzled
-__host__ __device__ constexpr int epi_bufs_per_warp(int tma_mode) { return tma_mode == 3 ? 3 : (tma_mode != 0 ? 1 : 0); }
+__host__ __device__ constexpr int epi_bufs_per_warp(int tma_mode) { return tma_mode == 3 ? 3 : (tma_mode == 4 ? 2 : (tma_mode != 0 ? 1 : 0)); }
+__device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
 template <int BN>
 struct GemmSmem {
@@ -55,7 +67,7 @@ struct GemmSmem {
   static constexpr int kMaxStages = 8;
 };
 
-template <int BN, int A_MN, int B_MN>
+template <int BN, int A_MN, int B_MN, bool RS = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAdd,
@@ -187,8 +199,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // tiles, so that residual chunks can be requested ahead of the tile they belong to.
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
     const int ew = warp - 2, half = ew >> 2;      // half: which half of the tile's columns
-    const int n_in = ep.tma_mode == 3 ? 2 : (ep.tma_mode == 2 ? 1 : 0);
+    const int n_in = ep.tma_mode == 3 ? 2 : (ep.tma_mode == 2 || ep.tma_mode == 4 ? 1 : 0);
     const bool inplace = ep.tma_mode == 2;
+    constexpr bool rowstat = RS;       // tma_mode 4 is only ever launched on the RS instantiation
+    float rs1 = 0.f, rs2 = 0.f;
+    uint2 kb_nx = make_uint2(0xffffffffu, 0xffffffffu);
     uint8_t* my = staging + ew * epi_bufs_per_warp(ep.tma_mode) * kEpiBuf;
     uint8_t* out_buf = my + (inplace ? 0 : n_in) * kEpiBuf;
     uint64_t* in_bar = add_bar + ew * 2;
@@ -214,7 +229,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tma_load_2d(my + b * kEpiBuf, &tmAdd, &in_bar[b], col0, row0);
       }
     };
-    if (n_in == 2 && lane == 0) { issue_load(0); issue_load(1); }
+    auto fetch_keep = [&](int g) {        // this lane's 64 dropout keep bits of chunk g, consumed one chunk later
+      int row0, col0;
+      kb_nx = make_uint2(0xffffffffu, 0xffffffffu);
+      if (ep.rs_keep != nullptr && g < total && coords(g, row0, col0) && row0 + lane < M)
+        kb_nx = __ldg(reinterpret_cast<const uint2*>(ep.rs_keep + static_cast<long>(row0 + lane) * (N >> 3) + (col0 >> 3)));
+    };
+    if constexpr (rowstat) fetch_keep(0);
+    if (!inplace && lane == 0)
+      for (int k = 0; k < n_in; ++k) issue_load(k);
     int acc = 0;
     uint32_t acc_phase = 0, in_phase = 0;
     for (int g = 0; g < total; ++g) {
@@ -262,6 +285,33 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             q[j] = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
           }
         } else {
+          if constexpr (rowstat) {     // this thread = one output row, 64 columns
+            const int row = row0 + lane;
+            const uint32_t kb_lo = kb_nx.x, kb_hi = kb_nx.y;
+            fetch_keep(g + 1);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint4 hv = *reinterpret_cast<const uint4*>(in_buf + row_off + ((static_cast<uint32_t>(j) << 4) ^ sw));
+              const float4 g0 = __ldg(reinterpret_cast<const float4*>(ep.rs_gamma + col0 + 8 * j));
+              const float4 g1 = __ldg(reinterpret_cast<const float4*>(ep.rs_gamma + col0 + 8 * j + 4));
+              const uint32_t* rr = j < 4 ? r0 + 8 * j : r1 + 8 * (j - 4);
+              const uint32_t kb = ((j < 4 ? kb_lo : kb_hi) >> (8 * (j & 3))) & 0xffu;
+              const float d[8] = {__uint_as_float(rr[0]) * ep.alpha, __uint_as_float(rr[1]) * ep.alpha, __uint_as_float(rr[2]) * ep.alpha,
+                                  __uint_as_float(rr[3]) * ep.alpha, __uint_as_float(rr[4]) * ep.alpha, __uint_as_float(rr[5]) * ep.alpha,
+                                  __uint_as_float(rr[6]) * ep.alpha, __uint_as_float(rr[7]) * ep.alpha};
+              const float hf[8] = {bf16lo(hv.x), bf16hi(hv.x), bf16lo(hv.y), bf16hi(hv.y), bf16lo(hv.z), bf16hi(hv.z), bf16lo(hv.w), bf16hi(hv.w)};
+              const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                rs1 = fmaf(gm[e], ((kb >> e) & 1u) ? d[e] : 0.f, rs1);
+                rs2 = fmaf(d[e], hf[e], rs2);
+              }
+            }
+            if (c == cpt - 1) {
+              if (row < M) ep.rs_part[static_cast<long>(row) * ep.rs_parts + 2 * ((col0 - half * (BN / 2)) / BN) + half] = make_float2(rs1 * ep.rs_keep_scale, rs2);
+              rs1 = 0.f; rs2 = 0.f;
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             q[j] = make_uint4(pack_bf16x2(__uint_as_float(r0[8 * j]) * ep.alpha, __uint_as_float(r0[8 * j + 1]) * ep.alpha),
@@ -428,12 +478,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 constexpr int kMaxDynSmem = 232448;      // 227 KB per CTA on sm_100
 constexpr int kBarrierBytes = 512;
 
-template <int BN, int A_MN, int B_MN>
+template <int BN, int A_MN, int B_MN, bool RS = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmAdd,
                        const EpiParams& ep, int M, int N, int K, int splits, int max_ctas, int a_f16, int b_f16,
                        cudaStream_t stream) {
   using S = GemmSmem<BN>;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, RS>;
   // shared memory: operand ring | epilogue staging | barriers.  The ring takes what the staging buffers leave.
   const int staging = kEpiWarps * epi_bufs_per_warp(ep.tma_mode) * kEpiBuf;
   int stages = (kMaxDynSmem - 1024 - kBarrierBytes - staging) / S::kStageBytes;
@@ -469,11 +519,15 @@ static bool tma_epilogue_enabled() {
 
 }  // namespace omlm
 
-extern "C" int omlm_gemm16(const void* A, int a_f16, int a_mn_major, long lda, const void* B, int b_f16, int b_mn_major,
-                           long ldb, int M, int N, int K, void* out, int out_f32, long ldo,
-                           const float* addend, long ldadd, float alpha, int splits,
-                           int row_split, int row_valid, int n_valid, int block_n, int max_ctas,
-                           void* stream_) {
+namespace omlm {
+struct RowStatArgs { const void* hn; long ldhn; const void* keep_bits; const float* gamma; float keep_scale; float* part; int parts; };
+}
+
+static int gemm16_impl(const void* A, int a_f16, int a_mn_major, long lda, const void* B, int b_f16, int b_mn_major,
+                       long ldb, int M, int N, int K, void* out, int out_f32, long ldo,
+                       const float* addend, long ldadd, float alpha, int splits,
+                       int row_split, int row_valid, int n_valid, int block_n, int max_ctas,
+                       void* stream_, const omlm::RowStatArgs* rs) {
   using namespace omlm;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   OMLM_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem %d x %d x %d", M, N, K);
@@ -506,7 +560,20 @@ extern "C" int omlm_gemm16(const void* A, int a_f16, int a_mn_major, long lda, c
   // dense outputs leave through shared memory + TMA (see the kernel header); everything that remaps rows, reduces
   // atomically or is not 16-byte aligned keeps the per-thread path
   ep.tma_mode = 0;
+  ep.rs_gamma = nullptr; ep.rs_keep = nullptr; ep.rs_part = nullptr; ep.rs_keep_scale = 1.f; ep.rs_parts = 0;
   CUtensorMap tmOut = tmA, tmAdd = tmA;     // placeholders when unused (never dereferenced)
+  if (rs != nullptr) {
+    OMLM_CHECK_ARG(block_n == 256 && N % 256 == 0 && n_valid == N && !out_f32 && addend == nullptr && splits == 1 && row_split == 0 &&
+                   ep.vec_ok && rs->parts == 2 * (N / 256) && rs->ldhn % 8 == 0,
+                   "gemm row statistics: needs 256-wide tiles, N %% 256 == 0, a dense bf16 output and parts == N / 128");
+    rc = make_tmap_2d(&tmOut, 2, out, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 2, 64, 32);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tmAdd, 2, rs->hn, (uint64_t)N, (uint64_t)M, (uint64_t)rs->ldhn * 2, 64, 32);
+    if (rc) return rc;
+    ep.tma_mode = 4;
+    ep.rs_gamma = rs->gamma; ep.rs_keep = reinterpret_cast<const uint8_t*>(rs->keep_bits);
+    ep.rs_part = reinterpret_cast<float2*>(rs->part); ep.rs_keep_scale = rs->keep_scale; ep.rs_parts = rs->parts;
+  } else
   if (tma_epilogue_enabled() && splits == 1 && row_split == 0 && ep.vec_ok && (addend == nullptr || out_f32)) {
     const uint32_t cw = out_f32 ? 32 : 64;
     rc = make_tmap_2d(&tmOut, static_cast<int>(esz), out, (uint64_t)n_valid, (uint64_t)M, (uint64_t)ldo * esz, cw, 32);
@@ -519,6 +586,10 @@ extern "C" int omlm_gemm16(const void* A, int a_f16, int a_mn_major, long lda, c
     }
   }
   const int key = (block_n == 256 ? 4 : 0) | (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
+  if (ep.tma_mode == 4) {
+    OMLM_CHECK_ARG(key == 5, "gemm row statistics: only the A K-major / B MN-major 256-wide instantiation exists");
+    return launch_gemm<256, 0, 1, true>(tmA, tmB, tmOut, tmAdd, ep, M, N, K, splits, max_ctas, a_f16, b_f16, stream);
+  }
   switch (key) {
     case 0: return launch_gemm<128, 0, 0>(tmA, tmB, tmOut, tmAdd, ep, M, N, K, splits, max_ctas, a_f16, b_f16, stream);
     case 1: return launch_gemm<128, 0, 1>(tmA, tmB, tmOut, tmAdd, ep, M, N, K, splits, max_ctas, a_f16, b_f16, stream);
@@ -530,6 +601,24 @@ extern "C" int omlm_gemm16(const void* A, int a_f16, int a_mn_major, long lda, c
       set_last_error("gemm: operand majors (a_mn=%d, b_mn=%d) not instantiated", a_mn_major, b_mn_major);
       return 1;
   }
+}
+
+extern "C" int omlm_gemm16(const void* A, int a_f16, int a_mn_major, long lda, const void* B, int b_f16, int b_mn_major,
+                           long ldb, int M, int N, int K, void* out, int out_f32, long ldo,
+                           const float* addend, long ldadd, float alpha, int splits,
+                           int row_split, int row_valid, int n_valid, int block_n, int max_ctas,
+                           void* stream_) {
+  return gemm16_impl(A, a_f16, a_mn_major, lda, B, b_f16, b_mn_major, ldb, M, N, K, out, out_f32, ldo, addend, ldadd, alpha, splits,
+                     row_split, row_valid, n_valid, block_n, max_ctas, stream_, nullptr);
+}
+
+extern "C" int omlm_gemm16_rowstat(const void* A, int a_f16, int a_mn_major, long lda, const void* B, int b_f16, int b_mn_major,
+                                   long ldb, int M, int N, int K, void* out_bf16, long ldo, const void* hn_bf16, long ldhn,
+                                   const void* keep_bits, const float* gamma, float keep_scale, float* part, int parts,
+                                   int max_ctas, void* stream_) {
+  omlm::RowStatArgs rs{hn_bf16, ldhn, keep_bits, gamma, keep_scale, part, parts};
+  return gemm16_impl(A, a_f16, a_mn_major, lda, B, b_f16, b_mn_major, ldb, M, N, K, out_bf16, 0, ldo, nullptr, 0, 1.f, 1,
+                     0, 0, N, 256, max_ctas, stream_, &rs);
 }
 
 extern "C" int omlm_gemm_bf16(const void* A, int a_mn_major, long lda, const void* B, int b_mn_major,

@@ -297,10 +297,9 @@ class Engine:
             ws.update(
                 dlogits=[E(max(pl.B * c, 1), self.Cp[s]) for (s, qi, c, b0) in pl.groups],
                 dxf=E(max(pl.rows_total, 1), d), dx=[E(M, d, dt=f32) for _ in range(2)], dx_bf=E(M, d),
-                dhn=E(M, Fp), rowstat=E(M, 2, dt=f32), du=E(M, 2 * Fp), dxn=E(M, d), dxraw=E(M, d),
+                dhn=E(M, Fp), rowstat=E(M, Fp // 128, 2, dt=f32), du=E(M, 2 * Fp), dxn=E(M, d), dxraw=E(M, d),
                 d_o=E(M, HD), dqn=E(M, HD, dt=f32), dkvn=E(M, 128, dt=f32), dsum=E(M * h, dt=f32),
                 dq_raw=E(M, HD), dkv_raw=E(M, 128), dtable=E(h, pl.N, dt=f32),
-                dgin=E(Fp, dt=f32), dconv=E(2 * Fp, 3, dt=f32),
                 rp_d0=E(pl.N, self.Hr, dt=f32), rp_d1=E(pl.N, self.Hr, dt=f32), rp_dz3=E(pl.N, 3 * self.Hr),
             )
         self._ws[key] = ws
@@ -451,14 +450,21 @@ class Engine:
             p, pk = f"transformer.layers.{l}.", self.pk[l]
             xa, xm = x[2 * l], x[2 * l + 1]
             # ---- conv feed-forward
-            lib.gemm(ws["dx_bf"], pk["w2_b"], ws["dhn"], b_mn=True, M=M, N=Fp, K=d, block_n=self._bn_for(M, Fp, d), max_ctas=self.bwd_max_ctas)
+            # d_hn = dx W2 with the LayerNorm-backward row sums (against the saved hn) taken in the GEMM's epilogue
             fk = self.ffk
-            self._wgrad(ws["dx_bf"], ws["hn"][l], gv[p + fk["w2"]], d, Fp, n_valid=F)
+            keep = ws["keep"][l] if drop_p > 0 else None
+            if Fp % 256 == 0:
+                lib.gemm_rowstat(ws["dx_bf"], pk["w2_b"], ws["dhn"], ws["hn"][l], pk["gin"], ws["rowstat"], b_mn=True, M=M, N=Fp, K=d,
+                                 keep_bits=keep, keep_scale=1.0 / (1.0 - drop_p) if drop_p > 0 else 1.0, max_ctas=self.bwd_max_ctas)
+                parts = Fp // 128
+            else:
+                lib.gemm(ws["dx_bf"], pk["w2_b"], ws["dhn"], b_mn=True, M=M, N=Fp, K=d, block_n=self._bn_for(M, Fp, d), max_ctas=self.bwd_max_ctas)
+                parts = 0
+            # (the tile kernel runs right behind the GEMM that wrote dhn, while dhn is still in L2; the weight gradient after it)
             lib.ffn_mid_bwd(ws["dhn"], ws["hn"][l], ws["u"][l], ws["st_i"][l], pk["conv"], pk["gin"], ws["rowstat"], ws["du"],
-                            ws["dgin"], ws["dconv"], B, N, F, Fp, drop_p, keep_bits=ws["keep"][l] if drop_p > 0 else None)
-            lib.unpack_add(ws["dgin"], 1, Fp, gv[p + fk["gin"]], F, 1, F)
-            if fk["conv"] is not None:
-                lib.unpack_add(ws["dconv"], 2 * Fp, 3, gv[p + fk["conv"]], 3, 2 * F, 3, split_dst=-1, split_src=F)
+                            gv[p + fk["gin"]], gv[p + fk["conv"]] if fk["conv"] is not None else None, B, N, F, Fp, drop_p,
+                            keep_bits=keep, rowstat_parts=parts)
+            self._wgrad(ws["dx_bf"], ws["hn"][l], gv[p + fk["w2"]], d, Fp, n_valid=F)
             lib.gemm(ws["du"], pk["w1_b"], ws["dxn"], b_mn=True, M=M, N=d, K=2 * Fp, block_n=self._bn_for(M, d, 2 * Fp), max_ctas=self.bwd_max_ctas)
             self._wgrad(ws["du"], ws["xn2"][l], gv[p + fk["w1"]], 2 * Fp, d, row_split=-1, row_valid=F)
             lib.layernorm_bwd(ws["dxn"], xm, ws["st_f"][l], pv[p + fk["g1"]], dxb, gv[p + fk["g1"]], dres=dxa, dx_bf16=ws["dx_bf"])

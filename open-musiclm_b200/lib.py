@@ -233,10 +233,26 @@ def ffn_norm_fwd(h, rowsum, gamma, hn, stats, F, Fp, drop_p=0.0, seed=None, laye
          _I(F), _I(Fp), _F(drop_p), _p(seed), _I(layer), _I(int(h.dtype == torch.float16)), _stream())
 
 
-def ffn_mid_bwd(dhn, hn, u, stats, conv_w, gamma, rowstat, du, dgamma, dconv_w, B, N, F, Fp, drop_p=0.0, keep_bits=None):
+def ffn_mid_bwd(dhn, hn, u, stats, conv_w, gamma, rowstat, du, dgamma, dconv_w, B, N, F, Fp, drop_p=0.0, keep_bits=None, rowstat_parts=0):
+    """dgamma [F] / dconv_w [2F, 3] (or None) are accumulated in the parameters' own layouts; rowstat_parts > 0: rowstat
+    holds the partial row sums written by gemm_rowstat, else it is a [M, 2] scratch."""
     assert u.dtype in _T16 and hn.dtype == dhn.dtype == du.dtype == torch.bfloat16
-    call("omlm_ffn_mid_bwd", _p(dhn), _p(hn), _p(u), _p(stats), _p(conv_w), _p(gamma), _p(keep_bits), _p(rowstat), _p(du),
+    assert dgamma.numel() == F and (dconv_w is None or dconv_w.numel() == 6 * F)
+    call("omlm_ffn_mid_bwd", _p(dhn), _p(hn), _p(u), _p(stats), _p(conv_w), _p(gamma), _p(keep_bits), _p(rowstat), _I(rowstat_parts), _p(du),
          _p(dgamma), _p(dconv_w), _I(B), _I(N), _I(F), _I(Fp), _F(drop_p), _I(int(u.dtype == torch.float16)), _stream())
+
+
+def gemm_rowstat(a, b, out, hn, gamma, part, *, b_mn=False, M=None, N=None, K=None, keep_bits=None, keep_scale=1.0, max_ctas=0):
+    """out = a b^T (dense bf16 [M, N], 256-wide tiles) + per-row partial sums against hn in the epilogue (omlm_gemm16_rowstat)."""
+    assert a.dtype in _T16 and b.dtype == a.dtype and out.dtype == hn.dtype == torch.bfloat16 and part.dtype == torch.float32
+    M = a.shape[0] if M is None else M
+    K = a.shape[1] if K is None else K
+    N = (b.shape[1] if b_mn else b.shape[0]) if N is None else N
+    assert part.numel() == M * (N // 128) * 2
+    call("omlm_gemm16_rowstat", _p(a), _I(int(a.dtype == torch.float16)), _I(0), _L(a.stride(0)), _p(b), _I(int(b.dtype == torch.float16)),
+         _I(int(b_mn)), _L(b.stride(0)), _I(M), _I(N), _I(K), _p(out), _L(out.stride(0)), _p(hn), _L(hn.stride(0)), _p(keep_bits), _p(gamma),
+         _F(keep_scale), _p(part), _I(N // 128), _I(max_ctas), _stream())
+    return out
 
 
 def cross_entropy(logits, labels, C, loss_acc, *, grad_scale=0.0, dlogits=None, ignore_index=-100, label_stride=1, rows=None):

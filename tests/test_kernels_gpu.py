@@ -307,13 +307,35 @@ def test_ffn_up_fused_and_mid_bwd(lib, B, N, d, F_, drop_p, adt):
     dhn[:, :F_] = torch.randn(M, F_, device=DEV).bfloat16()
     ref.backward(dhn[:, :F_].float())
     du = torch.empty(M, 2 * Fp, device=DEV, dtype=torch.bfloat16); rowstat = torch.empty(M, 2, device=DEV)
-    dg = torch.full((Fp,), float("nan"), device=DEV); dcw = torch.full((2 * Fp, 3), float("nan"), device=DEV)   # overwritten by the call
+    # parameter gradients are accumulated (+=) in the parameters' own layouts: start from a known non-zero value
+    dg = torch.full((F_,), 0.5, device=DEV); dcw = torch.full((2 * F_, 3), -0.25, device=DEV)
     lib.ffn_mid_bwd(dhn, hn_b, u, stats, cwp, gp, rowstat, du, dg, dcw, B, N, F_, Fp, drop_p, keep_bits=kbits if drop_p > 0 else None)
     assert rel(du[:, cols], uf.grad) < 1.5e-2
-    assert rel(dg[:F_], gr.grad) < 8e-3
-    dcw_c = torch.zeros(2 * F_, 3, device=DEV)
-    lib.unpack_add(dcw, 2 * Fp, 3, dcw_c, 3, 2 * F_, 3, split_dst=-1, split_src=F_)
-    assert rel(dcw_c, cwr.grad) < 1.5e-2
+    assert rel(dg - 0.5, gr.grad) < 8e-3
+    assert rel(dcw + 0.25, cwr.grad) < 1.5e-2
+    if Fp % 256 == 0:
+        # the same backward with the row sums taken in the epilogue of the GEMM that produces dhn (omlm_gemm16_rowstat):
+        # dhn = dx W2 for a random dx; partial sums per 128-column half tile against fp32 torch
+        dx = torch.randn(M, d, device=DEV).bfloat16()
+        w2 = ((torch.rand(d, Fp, device=DEV) * 2 - 1) / math.sqrt(d)).bfloat16()
+        w2[:, F_:] = 0
+        dhn2 = torch.empty(M, Fp, device=DEV, dtype=torch.bfloat16)
+        part = torch.full((M, Fp // 128, 2), float("nan"), device=DEV)
+        ks = 1.0 / (1.0 - drop_p) if drop_p > 0 else 1.0
+        lib.gemm_rowstat(dx, w2, dhn2, hn_b, gp, part, b_mn=True, M=M, N=Fp, K=d, keep_bits=kbits if drop_p > 0 else None, keep_scale=ks)
+        dref = dx.float() @ w2.float()
+        assert rel(dhn2, dref) < 4e-3
+        keep_f = ((kbits[:, :, None] >> torch.arange(8, device=DEV, dtype=torch.uint8)) & 1).float().reshape(M, Fp) if drop_p > 0 else torch.ones(M, Fp, device=DEV)
+        s1 = (gp[None] * keep_f * ks * dref).view(M, Fp // 128, 128).sum(-1)
+        s2 = (dref * hn_b.float()).view(M, Fp // 128, 128).sum(-1)
+        assert rel(part[..., 0], s1) < 2e-3 and rel(part[..., 1], s2) < 2e-3, (rel(part[..., 0], s1), rel(part[..., 1], s2))
+        # ... and the tile kernel fed with those partial sums equals the tile kernel with its own statistics pass
+        du_a = torch.empty_like(du); du_b = torch.empty_like(du)
+        dga = torch.zeros(F_, device=DEV); dgb = torch.zeros(F_, device=DEV); dca = torch.zeros(2 * F_, 3, device=DEV); dcb = torch.zeros(2 * F_, 3, device=DEV)
+        kb = kbits if drop_p > 0 else None
+        lib.ffn_mid_bwd(dhn2, hn_b, u, stats, cwp, gp, part, du_a, dga, dca, B, N, F_, Fp, drop_p, keep_bits=kb, rowstat_parts=Fp // 128)
+        lib.ffn_mid_bwd(dhn2, hn_b, u, stats, cwp, gp, rowstat, du_b, dgb, dcb, B, N, F_, Fp, drop_p, keep_bits=kb)
+        assert rel(du_a, du_b) < 3e-3 and rel(dga, dgb) < 3e-3 and rel(dca, dcb) < 3e-3, (rel(du_a, du_b), rel(dga, dgb), rel(dca, dcb))
 
 
 # ------------------------------------------------------------------------------------------------ loss / optimiser

@@ -186,13 +186,15 @@ int omlm_cross_entropy(const float* logits, long ld, const int* labels, int labe
 int omlm_grad_sumsq(const float* g, long n, float prescale, double* acc, void* stream);
 int omlm_adamw_step(float* p, const float* g, float* m, float* v, long n, long n_decay, const float* hyper,
                     const double* sumsq, void* stream);
-/* One launch for a whole table of omlm_pack jobs (the per-step refresh of the packed bf16 weights).  The table is
- * DEVICE memory; unit_start = running sum of ceil(rows_p * ceil(cols_p/4) / 256) over the preceding jobs,
- * total_units = that sum over all jobs.  njobs <= 512 per table.  dst_fmt: 0 = bf16, 1 = fp32, 2 = fp16. */
+/* One launch for a whole table of omlm_pack jobs (the per-step refresh of the packed 16-bit weights).  The table is
+ * DEVICE memory; unit_start = running sum of ceil(rows_p * ceil(cols_p/4) / 1024) over the preceding jobs,
+ * total_units = that sum over all jobs.  njobs <= 512 per table.  dst_fmt: 0 = bf16, 1 = fp32, 2 = fp16.
+ * dst2 (optional, NULL = none): a second destination of the same geometry in format dst2_fmt, written from the same
+ * read of src (the forward GEMMs take fp16 copies of the matrices whose bf16 copies the backward GEMMs read). */
 typedef struct {
-  const float* src; void* dst;
+  const float* src; void* dst; void* dst2;
   long src_ld, dst_ld, unit_start;
-  int rows_valid, cols_valid, rows_p, cols_p, split_dst, split_src, dst_fmt, reserved;
+  int rows_valid, cols_valid, rows_p, cols_p, split_dst, split_src, dst_fmt, dst2_fmt;
 } omlm_pack_job;
 int omlm_pack_multi(const omlm_pack_job* jobs_device, int njobs, long total_units, void* stream);
 /* canonical fp32 -> padded compute layout (bf16 or fp32) and gradient unpacking (+=). */

@@ -345,7 +345,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) issue_load(g + n_in);
       }
     }
-    if (lane == 0) tma_store_wait_all();
+    if (lane == 0) tma_store_wait_read<0>();   // the staging buffers have been read; the writes themselves complete with the grid
   } else {
     // ------------------------------------------------------------------ epilogue warps
     const int quarter = warp & 3;  // TMEM lane quarter this warp may read

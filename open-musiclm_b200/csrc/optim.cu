@@ -68,6 +68,56 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
 //                     w = r % 256, c = (r / 256) * 128 + w % 128, src row = (w / 128) * split_src + c, live iff c < split_src
 //      split_dst = 0: live iff r < rows_valid.
 template <typename OutT>
+__device__ __forceinline__ void store_quad(OutT* __restrict__ dst, long dst_ld, int r, int c, int cols_p, const float (&v)[4]) {
+  const bool vec_dst = ((dst_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((cols_p & 3) == 0);
+  OutT* d = dst + r * dst_ld + c;
+  if (vec_dst) {
+    if constexpr (sizeof(OutT) == 2) {
+      constexpr bool kHalf = std::is_same<OutT, __half>::value;
+      uint2 o; o.x = pack16x2<kHalf>(v[0], v[1]); o.y = pack16x2<kHalf>(v[2], v[3]);
+      *reinterpret_cast<uint2*>(d) = o;
+    } else {
+      *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (c + j < cols_p) {
+        if constexpr (std::is_same<OutT, __half>::value) d[j] = __float2half_rn(fminf(fmaxf(v[j], -65504.f), 65504.f));
+        else if constexpr (sizeof(OutT) == 2) d[j] = __float2bfloat16_rn(v[j]);
+        else d[j] = v[j];
+      }
+    }
+  }
+}
+__device__ __forceinline__ void store_quad_fmt(void* dst, int fmt, long dst_ld, int r, int c, int cols_p, const float (&v)[4]) {
+  if (fmt == kFmtF32) store_quad<float>(reinterpret_cast<float*>(dst), dst_ld, r, c, cols_p, v);
+  else if (fmt == kFmtF16) store_quad<__half>(reinterpret_cast<__half*>(dst), dst_ld, r, c, cols_p, v);
+  else store_quad<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(dst), dst_ld, r, c, cols_p, v);
+}
+
+// loads the 4 source values of quad i (zeros where the destination is padding); returns its destination (row, column)
+__device__ __forceinline__ void load_quad(long i, const float* __restrict__ src, long src_ld, int rows_valid, int cols_valid,
+                                          int cols_p, int split_dst, int split_src, int& r, int& c, float (&v)[4]) {
+  const int c4n = (cols_p + 3) >> 2;
+  const bool vec_src = ((src_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  r = static_cast<int>(i / c4n); c = static_cast<int>(i - static_cast<long>(r) * c4n) << 2;
+  int sr = r; bool live = r < rows_valid;
+  if (split_dst > 0) { const int half = r / split_dst, rr = r - half * split_dst; sr = half * split_src + rr; live = rr < split_src && sr < rows_valid; }
+  else if (split_dst < 0) { const int w = r & 255, ch = ((r >> 8) << 7) + (w & 127); sr = (w >> 7) * split_src + ch; live = ch < split_src && sr < rows_valid; }
+  v[0] = v[1] = v[2] = v[3] = 0.f;
+  if (live) {
+    if (vec_src && c + 3 < cols_valid) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(src + sr * src_ld + c));
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (c + j < cols_valid) v[j] = src[sr * src_ld + c + j];
+    }
+  }
+}
+
+template <typename OutT>
 __device__ __forceinline__ void pack_quad(long i, const float* __restrict__ src, long src_ld, int rows_valid, int cols_valid,
                                           OutT* __restrict__ dst, long dst_ld, int cols_p, int split_dst, int split_src) {
   // one call per 4 consecutive columns of a destination row
@@ -121,22 +171,39 @@ __global__ void pack_kernel(const float* __restrict__ src, long src_ld, int rows
 // All repacks of one optimiser step in ONE launch: the job table lives in device memory, work is cut into units of
 // 256 quads and blocks stride over the concatenated unit list (45 small launches -> 1 bandwidth-bound pass).
 constexpr int kPackMaxJobs = 512;
+constexpr int kPackUnit = 1024;      // quads per unit: 4 per thread, 256 apart (coalesced), all four loads in flight together
 __global__ void __launch_bounds__(256) pack_multi_kernel(const omlm_pack_job* __restrict__ jobs, int njobs, long total_units) {
   pdl_prologue();
   __shared__ long starts[kPackMaxJobs + 1];
+  __shared__ omlm_pack_job s_job;
   for (int j = threadIdx.x; j < njobs; j += blockDim.x) starts[j] = jobs[j].unit_start;
   if (threadIdx.x == 0) starts[njobs] = total_units;
   __syncthreads();
+  int cur = -1;
   for (long u = blockIdx.x; u < total_units; u += gridDim.x) {
     int lo = 0, hi = njobs - 1;
     while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (starts[mid] <= u) lo = mid; else hi = mid - 1; }
-    const omlm_pack_job jb = jobs[lo];
-    const long i = (u - jb.unit_start) * 256 + threadIdx.x;
+    if (lo != cur) {                  // (uniform across the block) fetch the job record once per job, not per thread
+      __syncthreads();
+      if (threadIdx.x == 0) s_job = jobs[lo];
+      __syncthreads();
+      cur = lo;
+    }
+    const omlm_pack_job& jb = s_job;
     const long total = static_cast<long>(jb.rows_p) * ((jb.cols_p + 3) >> 2);
-    if (i >= total) continue;
-    if (jb.dst_fmt == kFmtF32) pack_quad<float>(i, jb.src, jb.src_ld, jb.rows_valid, jb.cols_valid, reinterpret_cast<float*>(jb.dst), jb.dst_ld, jb.cols_p, jb.split_dst, jb.split_src);
-    else if (jb.dst_fmt == kFmtF16) pack_quad<__half>(i, jb.src, jb.src_ld, jb.rows_valid, jb.cols_valid, reinterpret_cast<__half*>(jb.dst), jb.dst_ld, jb.cols_p, jb.split_dst, jb.split_src);
-    else pack_quad<__nv_bfloat16>(i, jb.src, jb.src_ld, jb.rows_valid, jb.cols_valid, reinterpret_cast<__nv_bfloat16*>(jb.dst), jb.dst_ld, jb.cols_p, jb.split_dst, jb.split_src);
+    const long i0 = (u - jb.unit_start) * kPackUnit + threadIdx.x;
+    float v[4][4];
+    int r[4], c[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (i0 + k * 256 < total) load_quad(i0 + k * 256, jb.src, jb.src_ld, jb.rows_valid, jb.cols_valid, jb.cols_p, jb.split_dst, jb.split_src, r[k], c[k], v[k]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i0 + k * 256 < total) {
+        store_quad_fmt(jb.dst, jb.dst_fmt, jb.dst_ld, r[k], c[k], jb.cols_p, v[k]);
+        if (jb.dst2 != nullptr) store_quad_fmt(jb.dst2, jb.dst2_fmt, jb.dst_ld, r[k], c[k], jb.cols_p, v[k]);
+      }
+    }
   }
 }
 

@@ -217,10 +217,10 @@ class Engine:
             for l, pk in enumerate(self.pk):
                 p = f"transformer.layers.{l}."
                 fk = self.ffk
-                for sfx in (("", "_b") if pk["wq"] is not pk["wq_b"] else ("",)):
-                    tab.add(pv[p + "0.to_q.weight"], d, HD, d, pk["wq" + sfx], HD, d)
-                    tab.add(pv[p + fk["w1"]], d, 2 * F, d, pk["w1" + sfx], 2 * Fp, d, split_dst=-1, split_src=F)
-                    tab.add(pv[p + fk["w2"]], F, d, F, pk["w2" + sfx], d, Fp)
+                dual = pk["wq"] is not pk["wq_b"]       # fp16 forward copy + bf16 backward copy from ONE read of the matrix
+                tab.add(pv[p + "0.to_q.weight"], d, HD, d, pk["wq"], HD, d, dst2=pk["wq_b"] if dual else None)
+                tab.add(pv[p + fk["w1"]], d, 2 * F, d, pk["w1"], 2 * Fp, d, split_dst=-1, split_src=F, dst2=pk["w1_b"] if dual else None)
+                tab.add(pv[p + fk["w2"]], F, d, F, pk["w2"], d, Fp, dst2=pk["w2_b"] if dual else None)
                 tab.add(pv[p + "0.to_kv.weight"], d, 128, d, pk["wkv_b"], 128, d)
                 tab.add(pv[p + "0.to_out.0.weight"], HD, d, HD, pk["wo_b"], d, HD)
                 if fk["conv"] is not None:
@@ -228,9 +228,10 @@ class Engine:
                 tab.add(pv[p + fk["gin"]], F, 1, F, pk["gin"], 1, Fp)
             for s, seq in enumerate(self.seqs):
                 # [q, C, d] -> [q, Cp, d]: every head padded with zero rows
-                for dst in ((self.pk_logit[s], self.pk_logit_b[s]) if self.pk_logit[s] is not self.pk_logit_b[s] else (self.pk_logit[s],)):
-                    tab.add(pv[f"logit_weights.{s}"], d, seq.num_quantizers * self.C[s], d, dst.view(-1, d),
-                            seq.num_quantizers * self.Cp[s], d, split_dst=self.Cp[s], split_src=self.C[s])
+                dual = self.pk_logit[s] is not self.pk_logit_b[s]
+                tab.add(pv[f"logit_weights.{s}"], d, seq.num_quantizers * self.C[s], d, self.pk_logit[s].view(-1, d),
+                        seq.num_quantizers * self.Cp[s], d, split_dst=self.Cp[s], split_src=self.C[s],
+                        dst2=self.pk_logit_b[s].view(-1, d) if dual else None)
             self._pack_table = tab
         self._pack_table.run()
         if self.bias_type == "continuous":

@@ -276,10 +276,10 @@ def pack(src, src_ld, rows_valid, cols_valid, dst, rows_p, cols_p, split_dst=0, 
 
 
 class _PackJob(ctypes.Structure):
-    _fields_ = [("src", ctypes.c_void_p), ("dst", ctypes.c_void_p), ("src_ld", ctypes.c_long), ("dst_ld", ctypes.c_long),
-                ("unit_start", ctypes.c_long), ("rows_valid", ctypes.c_int), ("cols_valid", ctypes.c_int),
+    _fields_ = [("src", ctypes.c_void_p), ("dst", ctypes.c_void_p), ("dst2", ctypes.c_void_p), ("src_ld", ctypes.c_long),
+                ("dst_ld", ctypes.c_long), ("unit_start", ctypes.c_long), ("rows_valid", ctypes.c_int), ("cols_valid", ctypes.c_int),
                 ("rows_p", ctypes.c_int), ("cols_p", ctypes.c_int), ("split_dst", ctypes.c_int), ("split_src", ctypes.c_int),
-                ("dst_fmt", ctypes.c_int), ("reserved", ctypes.c_int)]
+                ("dst_fmt", ctypes.c_int), ("dst2_fmt", ctypes.c_int)]
 
 
 class PackTable:
@@ -290,15 +290,21 @@ class PackTable:
     def __init__(self, device):
         self.device, self.chunks, self.keep, self.tables = device, [[[], 0]], [], None
 
-    def add(self, src, src_ld, rows_valid, cols_valid, dst, rows_p, cols_p, split_dst=0, split_src=0):
+    UNIT = 1024         # quads (4 consecutive columns of a destination row) per work unit: kPackUnit in csrc/optim.cu
+
+    def add(self, src, src_ld, rows_valid, cols_valid, dst, rows_p, cols_p, split_dst=0, split_src=0, dst2=None):
+        """dst2: optional second destination with dst's geometry (another 16-bit format), written from the same read."""
         if len(self.chunks[-1][0]) == self.MAX_JOBS:
             self.chunks.append([[], 0])
         chunk = self.chunks[-1]
         dst_ld = cols_p if dst.dim() == 1 else dst.stride(0)
-        chunk[0].append(_PackJob(src.data_ptr(), dst.data_ptr(), src_ld, dst_ld, chunk[1], rows_valid, cols_valid, rows_p,
-                                 cols_p, split_dst, split_src, FMT[dst.dtype], 0))
-        self.keep.append((src, dst))
-        chunk[1] += (rows_p * ((cols_p + 3) // 4) + 255) // 256
+        if dst2 is not None:
+            assert dst2.shape == dst.shape and dst2.stride() == dst.stride() and dst2.element_size() == dst.element_size()
+        chunk[0].append(_PackJob(src.data_ptr(), dst.data_ptr(), dst2.data_ptr() if dst2 is not None else None, src_ld, dst_ld, chunk[1],
+                                 rows_valid, cols_valid, rows_p, cols_p, split_dst, split_src, FMT[dst.dtype],
+                                 FMT[dst2.dtype] if dst2 is not None else 0))
+        self.keep.append((src, dst, dst2))
+        chunk[1] += (rows_p * ((cols_p + 3) // 4) + self.UNIT - 1) // self.UNIT
         self.tables = None
 
     @property

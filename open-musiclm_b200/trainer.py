@@ -76,7 +76,10 @@ class HotPathTrainer:
         self.reducer = None
         self.allreduce_mode = "none (single GPU)"
         if self.world > 1:
-            self.reducer = BucketReducer(eng.arena_g, eng.grad_bucket_plan(), process_group, side_stream=torch.cuda.Stream())
+            # high priority: an all-reduce's CTAs are placed as soon as any SM frees up instead of after the compute kernels queued
+            # behind it (OMLM_NCCL_PRIO=0: same priority as the compute stream)
+            prio = -1 if os.environ.get("OMLM_NCCL_PRIO", "1") != "0" else 0
+            self.reducer = BucketReducer(eng.arena_g, eng.grad_bucket_plan(), process_group, side_stream=torch.cuda.Stream(priority=prio))
             nccl_ctas = int(os.environ.get("NCCL_MAX_CTAS", "0") or 0)
             eng.bwd_max_ctas = max(1, lib.num_sms() - nccl_ctas) if nccl_ctas > 0 else 0
             self.allreduce_mode = (f"{len(self.reducer.order)} buckets in backward order on a side stream, overlapped with the backward pass"

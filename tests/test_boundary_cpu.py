@@ -92,5 +92,5 @@ def test_pack_job_struct_matches_header():
         for part in decl.split(","):
             names.append(re.sub(r"[\s\*]", " ", part).split()[-1])
     assert names == [f[0] for f in lib._PackJob._fields_]
-    assert ctypes.sizeof(lib._PackJob) == 2 * 8 + 3 * 8 + 8 * 4
-    assert lib._PackJob.unit_start.offset == 32 and lib._PackJob.rows_valid.offset == 40
+    assert ctypes.sizeof(lib._PackJob) == 3 * 8 + 3 * 8 + 8 * 4
+    assert lib._PackJob.unit_start.offset == 40 and lib._PackJob.rows_valid.offset == 48

@@ -93,7 +93,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int n_tiles = (N + BN - 1) / BN;
   const int kb_total = (K + BK - 1) / BK;
   const int kb_per_split = (kb_total + splits - 1) / splits;
-  const int work_total = m_tiles * n_tiles * splits;
+  const int tiles_total = m_tiles * n_tiles;
+  const int work_total = tiles_total * splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -129,8 +130,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
-        const int split = w % splits;
-        const int tile = w / splits;
+        const int split = w / tiles_total;      // split-major order: the CTAs of a wave share one K range, so the
+        const int tile = w - split * tiles_total;   // operand slices of that range stay in L2 (tile-major thrashed it)
         const int n_blk = tile % n_tiles, m_blk = tile / n_tiles;
         const int kb0 = split * kb_per_split;
         const int kb1 = min(kb_total, kb0 + kb_per_split);
@@ -165,7 +166,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
-        const int split = w % splits;
+        const int split = w / tiles_total;
         const int kb0 = split * kb_per_split;
         const int kb1 = min(kb_total, kb0 + kb_per_split);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -353,7 +354,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
-      const int tile = w / splits;
+      const int tile = w % tiles_total;
       const int n_blk = tile % n_tiles, m_blk = tile / n_tiles;
       int row = m_blk * BM + quarter * 32 + lane;
       bool row_ok = row < M;

@@ -1,6 +1,7 @@
-"""Turn the CSV exports of tools/ncu_capture.sh into the small text/JSON files kept under profiles/.
-  python tools/ncu_summarize.py gpurun_out/ncu_hot_raw.csv [gpurun_out/ncu_src_walk.csv gpurun_out/ncu_src_ffnup.csv]
-Writes profiles/r01_ncu_summary.txt and profiles/r01_ncu_gemm_traffic.json (read by bench.py for roofline.traffic)."""
+"""Turn `ncu --page raw --csv` exports (tools/ncu_capture.sh) into the small text/JSON files kept under profiles/.
+  python tools/ncu_summarize.py <round-tag> <gemm_raw.csv> [other_raw.csv ...]
+Writes profiles/<tag>_ncu_summary.txt (one line per captured launch) and profiles/<tag>_ncu_gemm_traffic.json
+(DRAM bytes of the GEMM family over one full training step: read by bench.py for roofline.traffic)."""
 import collections
 import csv
 import json
@@ -14,75 +15,68 @@ COLS = [("gpu__time_duration.sum", "us"), ("dram__bytes_read.sum", "rd_MB"), ("d
         ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%"),
         ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor%"),
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
-        ("l1tex__t_sector_hit_rate.pct", "L1hit%"), ("lts__t_sector_hit_rate.pct", "L2hit%"),
-        ("smsp__inst_executed.sum", "warp_inst")]
-LAYERS, GEMMS_PER_LAYER = 6, 15
+        ("lts__t_sector_hit_rate.pct", "L2hit%"), ("smsp__inst_executed.sum", "warp_inst")]
 
 
 def short(name):
-    name = name.replace("void ", "")
-    return name.split("(")[0]
+    return name.replace("void ", "").replace("omlm::", "").split("(")[0]
+
+
+def to_unit(val, unit, want):
+    """ncu prints each metric in its own unit (byte / Kbyte / Mbyte, ns / us / ms): normalise."""
+    v = float(val.replace(",", ""))
+    scale = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
+    if want in ("MB", "us") and unit in scale:
+        return v * scale[unit]
+    return v
+
+
+def rows_of(path):
+    raw = list(csv.reader(open(path)))
+    hdr, units, rows = raw[0], raw[1], raw[2:]
+    ix = {c: hdr.index(c) for c, _ in COLS if c in hdr}
+    kn = hdr.index("Kernel Name")
+    out = []
+    for r in rows:
+        d = {"name": short(r[kn])}
+        for c, lbl in COLS:
+            if c in ix:
+                want = "MB" if lbl.endswith("_MB") else ("us" if lbl == "us" else "")
+                try:
+                    d[lbl] = to_unit(r[ix[c]], units[ix[c]], want)
+                except ValueError:
+                    d[lbl] = r[ix[c]]
+        out.append(d)
+    return out
 
 
 def main():
-    raw = list(csv.reader(open(sys.argv[1])))
-    hdr, rows = raw[0], raw[2:]
-    ix = {c: hdr.index(c) for c, _ in COLS if c in hdr}
-    kn = hdr.index("Kernel Name")
-    out = ["# ncu --set full --clock-control none, one depth-1 coarse training step at the bench shapes (B=16, N=1024, d=1024)",
-           "# launch order; per-launch values (times under ncu are cold-cache and serialised: use the shares, not the absolutes)",
-           "kernel | " + " | ".join(lbl for c, lbl in COLS if c in ix)]
-    gemm = []
-    for r in rows:
-        vals = []
-        for c, lbl in COLS:
-            if c in ix:
-                v = r[ix[c]]
-                try:
-                    v = f"{float(v):.6g}"
-                except ValueError:
-                    pass
-                vals.append(v)
-        out.append(short(r[kn]) + " | " + " | ".join(vals))
-        if "gemm_bf16_kernel" in r[kn] or "gemm_ffn_up_kernel" in r[kn]:
-            gemm.append(dict(name=short(r[kn]), us=float(r[ix["gpu__time_duration.sum"]]), grid=int(r[ix["launch__grid_size"]]),
-                             mb=float(r[ix["dram__bytes_read.sum"]]) + float(r[ix["dram__bytes_write.sum"]])))
-    # GEMM family traffic, scaled from the depth-1 capture to the 6-layer bench step: the per-layer GEMMs are the
-    # 15 launches between the rel-pos MLP / logit-head launches (5 forward incl. the fused FFN-up, 10 backward)
-    n = len(gemm)
-    heads = [g for i, g in enumerate(gemm) if i < 2 or 7 <= i < 16 or i >= n - 4]     # rel-pos fwd, logits fwd+bwd, rel-pos bwd
-    layer = [g for i, g in enumerate(gemm) if not (i < 2 or 7 <= i < 16 or i >= n - 4)]
-    assert len(layer) == GEMMS_PER_LAYER, (len(layer), n)
-    total_mb = LAYERS * sum(g["mb"] for g in layer) + sum(g["mb"] for g in heads)
-    launches = LAYERS * len(layer) + len(heads)
-    traffic = dict(source="profiles/r01_ncu_hot_raw.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)",
-                   launches_per_step=launches, family_mbytes_per_step=total_mb, bytes_per_launch=total_mb * 1e6 / launches,
-                   per_layer=[dict(name=g["name"], grid=g["grid"], us=g["us"], mbytes=g["mb"]) for g in layer])
-    json.dump(traffic, open(os.path.join(ROOT, "profiles", "r01_ncu_gemm_traffic.json"), "w"), indent=1)
-    out.append("")
-    out.append(f"GEMM family DRAM traffic scaled to the 6-layer step: {total_mb:.0f} MB over {launches} launches = "
-               f"{total_mb / launches:.1f} MB per launch")
-    for f in sys.argv[2:]:
-        src = list(csv.reader(open(f)))
-        h, body = src[1], src[2:]
-        isrc, iex, ist = h.index("Source"), h.index("Instructions Executed"), h.index("Warp Stall Sampling (All Samples)")
-        hist, stall = collections.Counter(), collections.Counter()
-        for r in body:
-            try:
-                e, t = int(r[iex] or 0), int(r[ist] or 0)
-            except (ValueError, IndexError):
-                continue
-            p = r[isrc].split()
-            op = p[1] if p and p[0].startswith("@") and len(p) > 1 else (p[0] if p else "?")
-            op = op.split(".")[0]
-            hist[op] += e; stall[op] += t
-        tot = sum(hist.values())
-        out.append("")
-        out.append(f"## SASS opcode mix, {os.path.basename(f)} (warp instructions executed, % of kernel, stall samples)")
-        for op, c in hist.most_common(16):
-            out.append(f"{op:10s} {c:>12d} {100.0 * c / tot:5.1f}%  {stall[op]}")
-    open(os.path.join(ROOT, "profiles", "r01_ncu_summary.txt"), "w").write("\n".join(out) + "\n")
-    print("\n".join(out[-40:]))
+    tag, gemm_csv, others = sys.argv[1], sys.argv[2], sys.argv[3:]
+    lines = [f"# ncu --set full --clock-control none; per-launch values (times under ncu are cold-cache and serialised: use the shares, not the absolutes)",
+             "kernel | " + " | ".join(lbl for _, lbl in COLS)]
+    fmt = lambda d: d["name"] + " | " + " | ".join(f"{d[lbl]:.6g}" if isinstance(d.get(lbl), float) else str(d.get(lbl, "")) for _, lbl in COLS)
+    g = rows_of(gemm_csv)
+    gem = [d for d in g if "gemm_bf16_kernel" in d["name"] or "gemm_ffn_up_kernel" in d["name"]]
+    lines.append(f"## GEMM family, every launch of one full cfg2 training step ({len(gem)} launches)")
+    lines += [fmt(d) for d in gem]
+    total_mb = sum(d["rd_MB"] + d["wr_MB"] for d in gem)
+    total_us = sum(d["us"] for d in gem)
+    by = collections.OrderedDict()
+    for d in gem:
+        a = by.setdefault(d["name"], [0, 0.0, 0.0, 0.0]); a[0] += 1; a[1] += d["us"]; a[2] += d["rd_MB"] + d["wr_MB"]; a[3] += d["tensor%"] * d["us"]
+    lines.append("")
+    lines.append(f"GEMM family over the step: {len(gem)} launches, {total_us:.0f} us under ncu, {total_mb:.0f} MB DRAM = {total_mb / len(gem):.1f} MB per launch")
+    for k, (n, us, mb, tw) in by.items():
+        lines.append(f"  {k:42s} n={n:3d}  {us:8.1f} us  {mb:8.0f} MB  tensor-pipe active (time-weighted) {tw / us:5.1f}%")
+    traffic = dict(source=f"profiles/{tag}_ncu_summary.txt (ncu --set full over every GEMM launch of one cfg2 step, dram__bytes_read.sum + dram__bytes_write.sum)",
+                   launches_per_step=len(gem), family_mbytes_per_step=total_mb, bytes_per_launch=total_mb * 1e6 / len(gem), family_us_under_ncu=total_us)
+    json.dump(traffic, open(os.path.join(ROOT, "profiles", f"{tag}_ncu_gemm_traffic.json"), "w"), indent=1)
+    for f in others:
+        lines.append("")
+        lines.append(f"## {os.path.basename(f)}")
+        lines += [fmt(d) for d in rows_of(f)]
+    open(os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.txt"), "w").write("\n".join(lines) + "\n")
+    print("\n".join(lines[-30:]))
 
 
 if __name__ == "__main__":

@@ -256,16 +256,26 @@ class Engine:
                                 f"(valid ids: 0..codebook_size, or the pad id at quantizer-0 positions)")
 
     # ------------------------------------------------------------------------------------------ plans / workspaces
+    _MAX_SHAPES = 8       # plans / workspaces kept (least recently used shapes are dropped: their HBM returns to torch)
+
     def plan(self, B, n_tok) -> _Plan:
         key = (B, tuple(n_tok))
-        if key not in self._plans:
-            self._plans[key] = _Plan(self, B, n_tok, self.dev)
-        return self._plans[key]
+        pl = self._plans.pop(key, None)
+        if pl is None:
+            pl = _Plan(self, B, n_tok, self.dev)
+        self._plans[key] = pl                       # (re-)inserted last = most recently used
+        while len(self._plans) > self._MAX_SHAPES:
+            self._plans.pop(next(iter(self._plans)))
+        return pl
 
     def workspace(self, pl: _Plan, train: bool):
         key = (pl.B, tuple(pl.n_tok), train)
         if key in self._ws:
-            return self._ws[key]
+            ws = self._ws.pop(key)
+            self._ws[key] = ws                      # most recently used
+            return ws
+        while len(self._ws) >= self._MAX_SHAPES:
+            self._ws.pop(next(iter(self._ws)))
         dev, bf, f32, a16 = self.dev, torch.bfloat16, torch.float32, self.a16
         M, d, HD, Fp, h = pl.M, self.d, self.HD, self.Fp, self.h
         E = lambda *shape, dt=bf: torch.empty(*shape, device=dev, dtype=dt)
@@ -576,6 +586,10 @@ class _ApiFunction(torch.autograd.Function):
         eng.forward_core(pl, ws, src_row, key_mask, need_grad, wanted, drop)
         ctx.eng, ctx.pl, ctx.src_row, ctx.key_mask, ctx.wanted, ctx.drop = eng, pl, src_row, key_mask, sorted(wanted), drop
         ctx.need_grad = need_grad
+        # the saved activations live in the shape's workspace, not in the graph: a second forward of the same shape before
+        # this call's backward would overwrite them -- remember which forward owns the workspace and check in backward
+        ws["generation"] = ws.get("generation", 0) + 1
+        ctx.ws, ctx.generation = ws, ws["generation"]
         outs = tuple(eng.gather_logits(pl, ws, s) for s in sorted(wanted))
         return outs
 
@@ -584,7 +598,11 @@ class _ApiFunction(torch.autograd.Function):
         eng, pl = ctx.eng, ctx.pl
         if not ctx.need_grad:
             raise RuntimeError("forward ran without gradient bookkeeping")
-        ws = eng.workspace(pl, True)
+        ws = ctx.ws
+        if ws.get("generation") != ctx.generation:
+            raise RuntimeError("open_musiclm_b200: the activations of this forward pass were overwritten by a later forward of the "
+                               "same shape (one workspace per shape): call backward() before the next forward, or use "
+                               "HotPathTrainer for gradient accumulation")
         with_grad = set()
         for s, g in zip(ctx.wanted, grads):
             if g is not None:

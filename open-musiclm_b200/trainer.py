@@ -238,8 +238,12 @@ class HotPathTrainer:
             self.steps += 1
             return self.loss_out
         key = tuple(tuple(t.shape) for mb in micro_batches for t in mb)
-        st = self._graphs.get(key)
+        st = self._graphs.pop(key, None)
+        if st is not None:
+            self._graphs[key] = st                   # most recently used
         if st is None:
+            while len(self._graphs) >= 8:            # least recently used shape: drop its graph, static buffers and workspaces
+                self._graphs.pop(next(iter(self._graphs)))
             st = self._graphs[key] = dict(count=0, graphs=None, static=[
                 [torch.empty(tuple(t.shape), dtype=torch.int64, device=eng.dev) for t in mb] for mb in micro_batches])
         for mb, smb in zip(micro_batches, st["static"]):
@@ -252,6 +256,9 @@ class HotPathTrainer:
             st["count"] += 1
         else:
             st["graphs"] = self._capture(st)
+            # a captured graph addresses the engine's plan / workspace buffers directly: keep them alive with the graph
+            # even if the engine's own shape cache evicts them
+            st["keepalive"] = (dict(eng._plans), dict(eng._ws))
             if st["graphs"] is None:
                 self.use_cuda_graph = False
                 self._step_body(st["static"])

@@ -308,6 +308,22 @@ def test_forward_with_cond_scale_and_token_id_bounds():
     m.engine.check_errors()                                  # the flag is cleared by the raise
 
 
+def test_api_backward_after_a_second_forward_is_refused():
+    """The reference-API path keeps the saved activations in one workspace per input shape: (model(a) + model(b)).backward()
+    would silently use b's activations for a's gradient, so the stale backward raises instead."""
+    import open_musiclm_b200 as O
+    torch.manual_seed(0)
+    m = O.create_semantic_transformer(dim=128, depth=1, heads=2, clap_codebook_size=64, semantic_codebook_size=64,
+                                      num_clap_quantizers=4, attn_dropout=0.0, ff_dropout=0.0).cuda()
+    g = torch.Generator().manual_seed(1)
+    mk = lambda: [torch.randint(0, 64, (2, 5), generator=g).cuda(), torch.randint(0, 64, (2, 9), generator=g).cuda()]
+    out_a = m(all_token_ids=mk())
+    out_b = m(all_token_ids=mk())
+    out_b[-1].float().sum().backward()                   # the latest forward: fine
+    with pytest.raises(RuntimeError, match="overwritten by a later forward"):
+        out_a[-1].float().sum().backward()
+
+
 def test_grad_accumulation_two_micro_batches():
     """grad_accum_every = 2 (the reference config uses 8; trainer.py:437-439 divides each micro-batch loss by it):
     the accumulated gradient equals the mean of the two micro-batch gradients, and in training mode the two

@@ -9,6 +9,7 @@ caches) and every further token costs one incremental step over
     per layer:  K/V cache [B, Nmax, 128] bf16  +  the last two pre-conv FFN rows [B, 2, 2Fp]  (CausalDSConv history)
 with the weight-streaming kernels of csrc/decode.cu, replayed from one CUDA graph per quantizer index.
 """
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -73,11 +74,41 @@ class DecodeSession:
         eng.build_bias_table(self.rp, N)
         self.table = self.rp["table"]
         self._graphs = {}
+        # the whole step as ONE persistent kernel (csrc/decode_fused.cu; bit-identical to the per-op sequence in step_ops);
+        # OMLM_DECODE_FUSED=0 keeps the per-op launches
+        self.fused = os.environ.get("OMLM_DECODE_FUSED", "1") != "0"
+        if self.fused:
+            pv = eng.pview
+            layers = []
+            for l in range(eng.L):
+                p, pk = f"transformer.layers.{l}.", eng.pk[l]
+                layers.append(dict(wq=pk["wq"], wkv=pk["wkv_b"], wo=pk["wo_b"], w1=pk["w1"], w2=pk["w2"], conv=pk["conv"], gin=pk["gin"],
+                                   g_attn=pv[p + "0.norm.gamma"], g_ff=pv[p + eng.ffk["g1"]], q_scale=pv[p + "0.q_scale"],
+                                   k_scale=pv[p + "0.k_scale"], cache=self.cache[l], conv_state=self.conv[l]))
+            self.layer_table, self._keep = lib.decode_layer_table(layers, dev)
+            self.hf32 = E(B, Fp, dt=f32)
+            self.barrier = torch.zeros(1, device=dev, dtype=torch.int32)
+            self.err_flag = torch.zeros(1, device=dev, dtype=torch.int32)
 
     # ------------------------------------------------------------------------------------------ one incremental step
     def step(self, qi_next: int):
         """Processes the position self.pos (embedding row self.next_row) through all layers and leaves the logits of
         head qi_next in self.logits."""
+        if not self.fused:
+            return self.step_ops(qi_next)
+        eng = self.eng
+        S = len(eng.seqs) - 1
+        lib.decode_step(self.layer_table, eng.L, self.B, eng.d, eng.h, eng.F, eng.Fp, self.n_max, eng.a16 == torch.float16, eng.table,
+                        self.next_row, self.table, self.pos, self.x[0], self.x[1], self.q_raw, self.kv_raw, self.o, self.h, self.hf32,
+                        eng.pk_logit[S][qi_next], eng.pview["transformer.norm.gamma"], self.logits, self.barrier, self.err_flag)
+
+    def check(self):
+        """Raises if a grid-wide barrier of the fused step timed out (synchronises)."""
+        if self.fused and int(self.err_flag.item()):
+            raise lib.OmlmError("open_musiclm_b200 generate: the fused decode step timed out at a grid barrier")
+
+    def step_ops(self, qi_next: int):
+        """The same step as separate launches (one per operation)."""
         eng, B = self.eng, self.B
         pv, d, HD, F, Fp, h = eng.pview, eng.d, eng.HD, eng.F, eng.Fp, eng.h
         xa, xm = self.x
@@ -214,6 +245,7 @@ class TokenConditionedTransformerWrapper(nn.Module):
                     sess.step_and_sample((p - 1) % q, p % q, top_k, temperature, allow(p), uni, eng.seed, use_graph=use_cuda_graph)
             eng.seed += 1
             sampled = torch.cat([prefix, sess.tokens[:, :n_new]], 1)
+            sess.check()
         else:
             sampled = prefix
         eos_mask = (sampled == eos).float()                                                         # utils.py:86-93

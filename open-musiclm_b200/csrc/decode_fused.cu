@@ -12,6 +12,11 @@
 // products + butterfly, conv / GEGLU, the 4 x 32 tree of the inner-LayerNorm row sums, the attention of
 // attn_decode_kernel), so both paths produce bit-identical logits (tests/test_decode_gpu.py compares them).
 //
+// Status: opt-in (OMLM_DECODE_FUSED=1).  Measured on B200 (10 s three-stage generation, batch 1): 0.68 ms per step
+// against 0.62 ms for the CUDA-graph replay of the per-op kernels -- ncu shows the step waiting at CTA barriers behind
+// single-warp sections (LayerNorm statistics, the row-sum tree, lane-0 epilogues) and instruction-cache misses of the
+// batch-unrolled loops; the launches it saves were not the bound.  Kept as the base for a batched-decode version.
+//
 // Replaces the loop body of TokenConditionedTransformerWrapper.generate (open_musiclm.py:300-319).
 #include "common.cuh"
 #include "../../include/omlm_b200.h"
@@ -68,26 +73,43 @@ __device__ __forceinline__ void df_rows_round(const float* __restrict__ x, long 
     *reinterpret_cast<uint32_t*>(sA + b * K + k) = df_pack(xv.x, xv.y, f16);
   }
 }
-// LayerNorm(x) * gamma (transformer.py:24-31)
+// LayerNorm(x) * gamma (transformer.py:24-31).  The rows are staged once in shared memory (sX, fp32 [B][K]); the
+// statistics are then formed from there in the per-op kernel's summation order (lane-strided sums, butterfly).
 __device__ __forceinline__ void df_rows_layernorm(const float* __restrict__ x, long ldx, const float* __restrict__ gamma, int B, int K,
-                                                  int f16, uint16_t* sA, float* s_mean, float* s_rstd) {
+                                                  int f16, uint16_t* sA, float* sX, float* s_mean, float* s_rstd) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < B * (K >> 2); i += blockDim.x) {
+    const int b = i / (K >> 2), k = (i - b * (K >> 2)) << 2;
+    *reinterpret_cast<float4*>(sX + b * K + k) = __ldcg(reinterpret_cast<const float4*>(x + b * ldx + k));
+  }
+  __syncthreads();
   for (int b = warp; b < B; b += kDfWarps) {
-    const float* xr = x + b * ldx;
+    const float* xr = sX + b * K;
     float s = 0.f;
-    for (int k = lane; k < K; k += 32) s += __ldcg(xr + k);
+    for (int k = lane; k < K; k += 32) s += xr[k];
     const float mean = warp_sum(s) / K;
     float q = 0.f;
-    for (int k = lane; k < K; k += 32) { const float d = __ldcg(xr + k) - mean; q += d * d; }
+    for (int k = lane; k < K; k += 32) { const float d = xr[k] - mean; q += d * d; }
     const float rstd = rsqrtf(warp_sum(q) / K + 1e-5f);
     if (lane == 0) { s_mean[b] = mean; s_rstd[b] = rstd; }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < B * (K >> 1); i += blockDim.x) {
     const int b = i / (K >> 1), k = (i - b * (K >> 1)) << 1;
-    const float2 xv = __ldcg(reinterpret_cast<const float2*>(x + b * ldx + k));
+    const float2 xv = *reinterpret_cast<const float2*>(sX + b * K + k);
     *reinterpret_cast<uint32_t*>(sA + b * K + k) =
         df_pack((xv.x - s_mean[b]) * s_rstd[b] * gamma[k], (xv.y - s_mean[b]) * s_rstd[b] * gamma[k + 1], f16);
+  }
+}
+
+// L2 prefetch of the two weight rows a warp will stream first in the NEXT stage, issued before the grid barrier: the rows do
+// not depend on the activations, so their DRAM latency hides behind the barrier and the next prologue.
+__device__ __forceinline__ void df_prefetch_rows(const uint16_t* W, long ldw, int row0, int row1, int K) {
+  const int lane = threadIdx.x & 31;
+  const int lines = (K * 2 + 127) >> 7;
+  for (int i = lane; i < 2 * lines; i += 32) {
+    const int r = i >= lines ? row1 : row0, ln = i >= lines ? i - lines : i;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(W + static_cast<long>(r) * ldw) + ln * 128));
   }
 }
 
@@ -101,30 +123,46 @@ __device__ __forceinline__ void df_dot2(const uint16_t* __restrict__ W, long ldw
 #pragma unroll
     for (int b = 0; b < kDfMaxB; ++b) acc[r][b] = 0.f;
   const int chunks = K >> 3;
-  for (int c = lane; c < chunks; c += 32) {
-    float w[2][8];
+  // four 16-byte chunks per row are requested before any of them is used (same accumulation order as one at a time):
+  // a step is a chain of ~30 such streaming loops, so every exposed DRAM round trip counts
+  for (int c0 = lane; c0 < chunks; c0 += 128) {
+    uint4 raw[4][2];
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      uint4 raw = make_uint4(0, 0, 0, 0);
-      const bool ok = r == 0 ? ok0 : ok1;
-      const int row = r == 0 ? row0 : row1;
-      if (ok) raw = __ldg(reinterpret_cast<const uint4*>(W + static_cast<long>(row) * ldw + c * 8));
-      const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + 32 * u;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { const float2 t = df_unpack(rw[q], f16); w[r][2 * q] = t.x; w[r][2 * q + 1] = t.y; }
+      for (int r = 0; r < 2; ++r) {
+        raw[u][r] = make_uint4(0, 0, 0, 0);
+        const bool ok = (r == 0 ? ok0 : ok1) && c < chunks;
+        const int row = r == 0 ? row0 : row1;
+        if (ok) raw[u][r] = __ldg(reinterpret_cast<const uint4*>(W + static_cast<long>(row) * ldw + c * 8));
+      }
     }
 #pragma unroll
-    for (int b = 0; b < kDfMaxB; ++b) {
-      if (b < B) {
-        const uint4 av = *reinterpret_cast<const uint4*>(sA + b * K + c * 8);
-        const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
-        float x[8];
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + 32 * u;
+      if (c < chunks) {
+        float w[2][8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { const float2 t = df_unpack(aw[q], f16); x[2 * q] = t.x; x[2 * q + 1] = t.y; }
+        for (int r = 0; r < 2; ++r) {
+          const uint32_t rw[4] = {raw[u][r].x, raw[u][r].y, raw[u][r].z, raw[u][r].w};
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
+          for (int q = 0; q < 4; ++q) { const float2 t = df_unpack(rw[q], f16); w[r][2 * q] = t.x; w[r][2 * q + 1] = t.y; }
+        }
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[r][b] = fmaf(x[e], w[r][e], acc[r][b]);
+        for (int b = 0; b < kDfMaxB; ++b) {
+          if (b < B) {
+            const uint4 av = *reinterpret_cast<const uint4*>(sA + b * K + c * 8);
+            const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
+            float x[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const float2 t = df_unpack(aw[q], f16); x[2 * q] = t.x; x[2 * q + 1] = t.y; }
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+              for (int e = 0; e < 8; ++e) acc[r][b] = fmaf(x[e], w[r][e], acc[r][b]);
+          }
+        }
       }
     }
   }
@@ -262,6 +300,7 @@ __global__ void __launch_bounds__(kDfThreads, 1) decode_step_kernel(const DfArgs
   uint16_t* sA = reinterpret_cast<uint16_t*>(df_smem);                 // [B][Kmax] activation rows (Kmax = max(d, Fp, HD))
   const int Kmax = max(max(a.d, a.Fp), a.HD);
   float* sc = reinterpret_cast<float*>(df_smem + static_cast<size_t>(a.B) * Kmax * 2);      // [n_max] attention scores
+  float* sX = sc + ((a.n_max + 3) & ~3);                                                                 // [B][d] fp32 rows for the LayerNorm prologues
   __shared__ float s_mean[kDfMaxB], s_rstd[kDfMaxB];
   __shared__ float sq[64], sk[64], sv[64], red[4];
   __shared__ float so[16][64];
@@ -278,13 +317,14 @@ __global__ void __launch_bounds__(kDfThreads, 1) decode_step_kernel(const DfArgs
     const int r = a.next_row[b];
     xa[i] = r >= 0 ? a.emb_table[static_cast<long>(r) * d + k] : 0.f;
   }
+  if (gwarp < HD / 2) df_prefetch_rows(a.layers[0].wq, d, 2 * gwarp, 2 * gwarp + 1, d);
   df_grid_sync(a.bar, epoch, a.err);
 
   for (int l = 0; l < a.L; ++l) {
     const DfLayer ly = a.layers[l];
     // ---- stage A: q = LayerNorm(x) Wq^T (fp16/bf16 operand format), [k | v] = x Wkv^T (bf16)
     {
-      df_rows_layernorm(xa, d, ly.g_attn, B, d, f16, sA, s_mean, s_rstd);
+      df_rows_layernorm(xa, d, ly.g_attn, B, d, f16, sA, sX, s_mean, s_rstd);
       __syncthreads();
       for (int it = gwarp; it < HD / 2; it += nwarps) {
         float acc[2][kDfMaxB];
@@ -310,6 +350,7 @@ __global__ void __launch_bounds__(kDfThreads, 1) decode_step_kernel(const DfArgs
           }
       }
     }
+    if (gwarp < d / 2) df_prefetch_rows(ly.wo, HD, 2 * gwarp, 2 * gwarp + 1, HD);      // stage C's rows (stage B streams no weights)
     df_grid_sync(a.bar, epoch, a.err);
     // ---- stage B: attention of the new position against the cache (one CTA per (sequence, head))
     for (int item = blockIdx.x; item < B * a.h; item += gridDim.x) df_attention(a, ly, item / a.h, item % a.h, sc, sq, sk, sv, red, so);
@@ -332,10 +373,11 @@ __global__ void __launch_bounds__(kDfThreads, 1) decode_step_kernel(const DfArgs
           }
       }
     }
+    if (gwarp < Fp) df_prefetch_rows(ly.w1, d, (gwarp >> 7) * 256 + (gwarp & 127), (gwarp >> 7) * 256 + 128 + (gwarp & 127), d);
     df_grid_sync(a.bar, epoch, a.err);
     // ---- stage D: u = LayerNorm(xm) W1^T; causal depthwise conv over (state, u); GEGLU (transformer.py:122-137)
     {
-      df_rows_layernorm(xm, d, ly.g_ff, B, d, f16, sA, s_mean, s_rstd);
+      df_rows_layernorm(xm, d, ly.g_ff, B, d, f16, sA, sX, s_mean, s_rstd);
       __syncthreads();
       const long ld = 2L * Fp;
       for (int it = gwarp; it < Fp; it += nwarps) {          // it = natural channel; rows: value g*256 + c, gate g*256 + 128 + c
@@ -364,6 +406,7 @@ __global__ void __launch_bounds__(kDfThreads, 1) decode_step_kernel(const DfArgs
         }
       }
     }
+    if (gwarp < d / 2) df_prefetch_rows(ly.w2, Fp, 2 * gwarp, 2 * gwarp + 1, Fp);
     df_grid_sync(a.bar, epoch, a.err);
     // ---- stage E: xa = xm + LayerNorm_F(h) W2^T  (inner LayerNorm from the per-128-channel sums, summed as the per-op path does)
     {
@@ -406,10 +449,12 @@ __global__ void __launch_bounds__(kDfThreads, 1) decode_step_kernel(const DfArgs
           }
       }
     }
+    if (l + 1 < a.L) { if (gwarp < HD / 2) df_prefetch_rows(a.layers[l + 1].wq, d, 2 * gwarp, 2 * gwarp + 1, d); }
+    else if (gwarp < a.C_pad / 2) df_prefetch_rows(a.w_logit, d, 2 * gwarp, 2 * gwarp + 1, d);
     df_grid_sync(a.bar, epoch, a.err);
   }
   // ---- logits of the requested head: LayerNorm(x) * gamma, then the head's rows
-  df_rows_layernorm(xa, d, a.g_final, B, d, f16, sA, s_mean, s_rstd);
+  df_rows_layernorm(xa, d, a.g_final, B, d, f16, sA, sX, s_mean, s_rstd);
   __syncthreads();
   for (int it = gwarp; it < (a.C_pad + 1) / 2; it += nwarps) {
     float acc[2][kDfMaxB];
@@ -446,7 +491,7 @@ extern "C" int omlm_decode_step(const omlm_decode_layer* layers_device, int L, i
   a.w_logit = reinterpret_cast<const uint16_t*>(w_logit); a.g_final = g_final; a.logits = logits; a.ld_logits = ld_logits;
   a.bar = barrier; a.err = err_flag; a.scale = scale;
   const int Kmax = std::max(std::max(d, Fp), heads * 64);
-  const int smem = B * Kmax * 2 + n_max * 4;
+  const int smem = B * Kmax * 2 + ((n_max + 3) & ~3) * 4 + B * d * 4;
   OMLM_CHECK_ARG(smem <= 200 * 1024, "decode_step: batch x width / context too large for shared memory (%d bytes)", smem);
   static int configured = 0;
   if (smem > configured) {

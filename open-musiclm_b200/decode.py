@@ -74,9 +74,11 @@ class DecodeSession:
         eng.build_bias_table(self.rp, N)
         self.table = self.rp["table"]
         self._graphs = {}
-        # the whole step as ONE persistent kernel (csrc/decode_fused.cu; bit-identical to the per-op sequence in step_ops);
-        # OMLM_DECODE_FUSED=0 keeps the per-op launches
-        self.fused = os.environ.get("OMLM_DECODE_FUSED", "1") != "0"
+        # OMLM_DECODE_FUSED=1: the whole step as ONE persistent kernel (csrc/decode_fused.cu; bit-identical to the per-op
+        # sequence in step_ops).  Off by default: measured on the 10 s three-stage generation it is slower than the
+        # graph-replayed per-op launches (5.0 s vs 4.0-4.4 s) -- its 31 stages are each bound by a single-warp prologue
+        # (LayerNorm statistics, row-sum tree) and a grid barrier, not by launch overhead.
+        self.fused = os.environ.get("OMLM_DECODE_FUSED", "0") == "1"
         if self.fused:
             pv = eng.pview
             layers = []

@@ -225,7 +225,8 @@ qk_l2norm_fwd_kernel(const __nv_bfloat16* __restrict__ q_raw, const __nv_bfloat1
   const int per_row = h + 2;
   const long long total = static_cast<long long>(M) * per_row;
   const bool active = gvec < total;
-  const long long row = active ? gvec / per_row : 0;
+  const long long row = !active ? 0 : (total <= 0x7fffffffLL ? static_cast<long long>(static_cast<unsigned int>(gvec) / static_cast<unsigned int>(per_row))
+                                                                : gvec / per_row);
   const int j = active ? static_cast<int>(gvec - row * per_row) : 0;
   const __nv_bfloat16* src;
   __nv_bfloat16* dst;
@@ -286,7 +287,9 @@ qk_l2norm_bwd_kernel(const float* __restrict__ dqn, const float* __restrict__ dk
        base += static_cast<long long>(gridDim.x) * (blockDim.x >> 3)) {
     const long long gvec = base + (threadIdx.x >> 3);
     const bool active = gvec < total;
-    const long long row = active ? gvec / per_row : 0;
+    // (32-bit division whenever the vector count allows it: the 64-bit form is a ~100-instruction routine per thread)
+    const long long row = !active ? 0 : (total <= 0x7fffffffLL ? static_cast<long long>(static_cast<unsigned int>(gvec) / static_cast<unsigned int>(per_row))
+                                                                  : gvec / per_row);
     const int j = active ? static_cast<int>(gvec - row * per_row) : 0;
     const __nv_bfloat16* src;
     const float* dsrc;

@@ -52,6 +52,26 @@ def test_gemm_fp16_operands(a_mn, b_mn):
         lib.gemm(a.bfloat16(), b, out, a_mn=a_mn, b_mn=b_mn)
 
 
+@pytest.mark.parametrize("block_n", [128, 256])
+@pytest.mark.parametrize("M,N,K", [(1000, 1032, 520), (128, 96, 64), (4100, 1024, 512)])
+def test_gemm_residual_tma_epilogue_tails(block_n, M, N, K):
+    """fp32 output + fp32 addend through the shared-memory staged epilogue (TMA loads of the addend, TMA stores) with row and
+    column tails, out of place and in place (128-wide tiles prefetch the addend two chunks ahead, 256-wide ones reuse one buffer)."""
+    from open_musiclm_b200 import lib
+    torch.manual_seed(M + N + K + block_n)
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = torch.randn(N, K, device="cuda").bfloat16()
+    X = torch.randn(M, N, device="cuda")
+    ref = X + A.float() @ B.float().t()
+    guard = torch.full((M + 2, N), 7.0, device="cuda")          # rows beyond M must stay untouched
+    out = guard[:M]
+    lib.gemm(A, B, out, addend=X, block_n=block_n)
+    assert _rel(out, ref) < 1e-5 and float((guard[M:] - 7.0).abs().max()) == 0.0
+    x2 = X.clone()
+    lib.gemm(A, B, x2, addend=x2, block_n=block_n)
+    assert _rel(x2, ref) < 1e-5
+
+
 def test_gemm_residual_and_splitk():
     from open_musiclm_b200 import lib
     torch.manual_seed(1)

@@ -94,17 +94,61 @@ def plan_buckets(layout: Dict[str, int], sizes: Dict[str, int], total: int, dept
     return out
 
 
+def shard_of(lo: int, hi: int, world: int, rank: int) -> Slice:
+    """The part of the arena slice [lo, hi) that `rank` owns after a reduce-scatter (equal parts, rank order)."""
+    n = hi - lo
+    assert n % world == 0, f"arena slice [{lo}, {hi}) is not divisible by the world size {world}"
+    return lo + rank * (n // world), lo + (rank + 1) * (n // world)
+
+
+def reduce_scatter_sum_(view: torch.Tensor, world: int, rank: int, group=None):
+    """In place: afterwards view[shard of rank] holds the sum over ranks of that part (the rest of `view` is undefined).
+    NCCL: one reduce-scatter (output = the rank's part of the input buffer, NCCL's in-place form).  Backends without
+    reduce-scatter (gloo, CPU tests): an all-reduce of the whole view."""
+    n = view.numel() // world
+    if dist.get_backend(group) == "nccl":
+        dist.reduce_scatter_tensor(view[rank * n:(rank + 1) * n], view, op=dist.ReduceOp.SUM, group=group)
+    else:
+        dist.all_reduce(view, op=dist.ReduceOp.SUM, group=group)
+
+
+def all_gather_(view: torch.Tensor, world: int, rank: int, group=None):
+    """In place: every rank's part of `view` (see shard_of) is distributed to all ranks."""
+    n = view.numel() // world
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(view, view[rank * n:(rank + 1) * n], group=group)
+    else:
+        parts = [torch.empty(n, dtype=view.dtype, device=view.device) for _ in range(world)]
+        dist.all_gather(parts, view[rank * n:(rank + 1) * n].clone(), group=group)
+        for r, part in enumerate(parts):
+            view[r * n:(r + 1) * n].copy_(part)
+
+
 class BucketReducer:
-    """Issues the per-bucket all-reduces.  `fire(trigger)` is called by the backward pass when the named point is
+    """Issues the per-bucket collectives.  `fire(trigger)` is called by the backward pass when the named point is
     reached; on CUDA the collective is enqueued on `side_stream` after an event recorded on the compute stream, and
     `join()` makes the compute stream wait for all of them (both work under CUDA-graph capture: fork / join).  On CPU
-    (gloo tests) everything is synchronous."""
+    (gloo tests) everything is synchronous.
+    scatter=False: all-reduce (every rank ends with the full summed arena).
+    scatter=True : reduce-scatter (rank r ends with the sum of ITS part of every slice, see shard_of): half the bytes on
+                   the wire; the optimiser then updates that part only and all-gathers the parameters (trainer.py)."""
 
-    def __init__(self, flat: torch.Tensor, plan, group=None, side_stream=None):
+    def __init__(self, flat: torch.Tensor, plan, group=None, side_stream=None, scatter=False):
         self.flat, self.plan, self.group, self.side = flat, {t: sl for t, sl in plan}, group, side_stream
         self.order = [t for t, _ in plan]
-        self.world, _ = world_info(group)
+        self.world, self.rank = world_info(group)
+        self.scatter = scatter
         self.fired: List[str] = []
+
+    def slices(self) -> List[Slice]:
+        """Every arena slice of the plan (they tile the arena)."""
+        return [s for t in self.order for s in self.plan[t]]
+
+    def _reduce(self, v: torch.Tensor):
+        if self.scatter:
+            reduce_scatter_sum_(v, self.world, self.rank, self.group)
+        else:
+            dist.all_reduce(v, op=dist.ReduceOp.SUM, group=self.group)
 
     def begin(self):
         self.fired = []
@@ -118,10 +162,10 @@ class BucketReducer:
             self.side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.side):
                 for v in views:
-                    dist.all_reduce(v, op=dist.ReduceOp.SUM, group=self.group)
+                    self._reduce(v)
         else:
             for v in views:
-                dist.all_reduce(v, op=dist.ReduceOp.SUM, group=self.group)
+                self._reduce(v)
 
     def join(self):
         if self.world > 1:

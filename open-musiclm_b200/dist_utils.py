@@ -52,7 +52,9 @@ def plan_buckets(layout: Dict[str, int], sizes: Dict[str, int], total: int, dept
     def span(names: Sequence[str]) -> Slice:
         lo = min(layout[n] for n in names)
         hi = max(layout[n] + sizes[n] for n in names)
-        return lo, hi
+        # parameters start on 64-element boundaries: take the padding behind the last one along, so that every slice
+        # length is a multiple of 64 (and with it of any power-of-two world size: reduce-scatter needs equal parts)
+        return lo, min(total, (hi + 63) // 64 * 64)
 
     mats = lambda l: [n for n in layout if n.startswith(f"transformer.layers.{l}.") and n.endswith("weight")]
     heads = [n for n in layout if n.startswith("logit_weights.")]

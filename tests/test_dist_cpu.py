@@ -128,3 +128,42 @@ def test_bucketed_allreduce_equals_one_allreduce(tmp_path):
     _, _, total = _toy_layout(4)
     ref = sum(torch.randn(total, generator=torch.Generator().manual_seed(100 + r)) for r in range(2))
     assert torch.equal(got, ref)
+
+
+def _shard_worker(rank, world, port, out):
+    """Sharded update on the toy arena: reduce-scatter buckets -> each rank owns its part of every slice -> a stand-in
+    'optimiser' (p -= 0.1 g) on the parts only -> all-gather of the parameters."""
+    from open_musiclm_b200.dist_utils import all_gather_, shard_of
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    layout, sizes, total = _toy_layout(4)
+    plan = plan_buckets(layout, sizes, total, 4, min_elems=500)
+    flat = torch.randn(total, generator=torch.Generator().manual_seed(100 + rank))
+    params = torch.arange(total, dtype=torch.float32) / total          # identical on every rank
+    red = BucketReducer(flat, plan, None, side_stream=None, scatter=True)
+    red.begin()
+    red.fire("heads")
+    for l in reversed(range(4)):
+        red.fire(f"layer{l}")
+    red.fire("tail")
+    red.join()
+    parts = [shard_of(lo, hi, world, rank) for lo, hi in red.slices()]
+    assert sum(b - a for a, b in parts) * world == total               # the parts of all ranks tile the arena
+    for a, b in parts:
+        params[a:b] -= 0.1 * flat[a:b]
+    for lo, hi in red.slices():
+        all_gather_(params[lo:hi], world, rank)
+    torch.save(params, out + f".{rank}")
+    dist.destroy_process_group()
+
+
+def test_sharded_update_equals_replicated_update(tmp_path):
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    out = str(tmp_path / "p.pt")
+    mp.spawn(_shard_worker, args=(2, port, out), nprocs=2, join=True)
+    _, _, total = _toy_layout(4)
+    gsum = sum(torch.randn(total, generator=torch.Generator().manual_seed(100 + r)) for r in range(2))
+    ref = torch.arange(total, dtype=torch.float32) / total - 0.1 * gsum
+    p0, p1 = torch.load(out + ".0"), torch.load(out + ".1")
+    assert torch.equal(p0, p1) and torch.equal(p0, ref)

@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include "../../include/omlm_b200.h"
+#include <stdlib.h>
 
 namespace omlm {
 
@@ -550,6 +551,10 @@ extern "C" int omlm_attn_bwd_tc(const void* qn, const void* kvn, const void* d_o
     if (smem_of(T) > kBtMaxSmem) break;
     tiles_per_chunk = T;
     if ((T >= 4 && units_of(T) * B <= 4L * num_sms()) || T == n_row_tiles) break;
+  }
+  if (const char* e = getenv("OMLM_ATTN_BWD_T")) {      // diagnostics: force the chunk length
+    const int T = atoi(e);
+    if (T >= 1 && T <= n_row_tiles && smem_of(T) <= kBtMaxSmem) tiles_per_chunk = T;
   }
   const int Wacc = wacc_of(tiles_per_chunk);
   const int smem_bytes = smem_of(tiles_per_chunk);

@@ -360,15 +360,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
           const int c = c2 * 32 + e;
-          const float x0 = fmaf(s[e], sc2, bp[-c] + kn[c]) - l2;
-          const float x1 = fmaf(s[e + 1], sc2, bp[-c - 1] + kn[c + 1]) - l2;
-          const float p0 = bt_ex2(x0), p1 = bt_ex2(x1);
+          // two keys per packed fp32x2 instruction (FADD2 / FFMA2 / FMUL2): same IEEE results, half the issue slots
+          const float2 bk = add2(make_float2(bp[-c], bp[-c - 1]), make_float2(kn[c], kn[c + 1]));
+          const float2 x = add2(fma2(make_float2(s[e], s[e + 1]), splat2(sc2), bk), splat2(-l2));
+          const float p0 = bt_ex2(x.x), p1 = bt_ex2(x.y);
           pp[e >> 1] = pack_bf16x2(p0, p1);
-          const float d0 = p0 * (dp[e] - dsm), d1 = p1 * (dp[e + 1] - dsm);
-          const uint32_t hi = pack_bf16x2(d0, d1);
+          const float2 d = mul2(make_float2(p0, p1), add2(make_float2(dp[e], dp[e + 1]), splat2(-dsm)));
+          const uint32_t hi = pack_bf16x2(d.x, d.y);
           const float2 hf = unpack_bf16x2(hi);
           dh[e >> 1] = hi;
-          dl[e >> 1] = pack_bf16x2(d0 - hf.x, d1 - hf.y);
+          const float2 lo = add2(d, make_float2(-hf.x, -hf.y));
+          dl[e >> 1] = pack_bf16x2(lo.x, lo.y);
         }
         if (c2 == 0 && t > 0) {
           // the previous tile's MMAs and its diagonal sums must be done with the P / dS buffers

@@ -270,10 +270,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
       for (int c = 0; c < 128; c += 4) {
         const float4 k4 = *reinterpret_cast<const float4*>(kn + c);   // warp-uniform address: one broadcast wavefront
-        s[c + 0] = fmaf(s[c + 0], sc2, bp[-c - 0] + k4.x);
-        s[c + 1] = fmaf(s[c + 1], sc2, bp[-c - 1] + k4.y);
-        s[c + 2] = fmaf(s[c + 2], sc2, bp[-c - 2] + k4.z);
-        s[c + 3] = fmaf(s[c + 3], sc2, bp[-c - 3] + k4.w);
+        {   // two keys per packed fp32x2 instruction (FADD2 / FFMA2): same IEEE results, half the issue slots
+          const float2 a01 = fma2(make_float2(s[c + 0], s[c + 1]), splat2(sc2), add2(make_float2(bp[-c - 0], bp[-c - 1]), make_float2(k4.x, k4.y)));
+          const float2 a23 = fma2(make_float2(s[c + 2], s[c + 3]), splat2(sc2), add2(make_float2(bp[-c - 2], bp[-c - 3]), make_float2(k4.z, k4.w)));
+          s[c + 0] = a01.x; s[c + 1] = a01.y; s[c + 2] = a23.x; s[c + 3] = a23.y;
+        }
         mx = fmaxf(mx, fmaxf(fmaxf(s[c], s[c + 1]), fmaxf(s[c + 2], s[c + 3])));
       }
       __syncwarp();
@@ -302,10 +303,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
 #pragma unroll
       for (int ch = 0; ch < 16; ++ch) {
-        const float p0 = ex2_fast(s[8 * ch + 0] - ref), p1 = ex2_fast(s[8 * ch + 1] - ref);
-        const float p2 = ex2_fast(s[8 * ch + 2] - ref), p3 = ex2_fast(s[8 * ch + 3] - ref);
-        const float p4 = ex2_fast(s[8 * ch + 4] - ref), p5 = ex2_fast(s[8 * ch + 5] - ref);
-        const float p6 = ex2_fast(s[8 * ch + 6] - ref), p7 = ex2_fast(s[8 * ch + 7] - ref);
+        const float2 nref = splat2(-ref);
+        const float2 x01 = add2(make_float2(s[8 * ch + 0], s[8 * ch + 1]), nref), x23 = add2(make_float2(s[8 * ch + 2], s[8 * ch + 3]), nref);
+        const float2 x45 = add2(make_float2(s[8 * ch + 4], s[8 * ch + 5]), nref), x67 = add2(make_float2(s[8 * ch + 6], s[8 * ch + 7]), nref);
+        const float p0 = ex2_fast(x01.x), p1 = ex2_fast(x01.y), p2 = ex2_fast(x23.x), p3 = ex2_fast(x23.y);
+        const float p4 = ex2_fast(x45.x), p5 = ex2_fast(x45.y), p6 = ex2_fast(x67.x), p7 = ex2_fast(x67.y);
         sum0 += p0 + p1; sum1 += p2 + p3; sum2 += p4 + p5; sum3 += p6 + p7;
         *reinterpret_cast<uint4*>(prow + (ch >> 3) * 16384 + (((ch & 7) ^ sw) << 4)) =
             make_uint4(pack_bf16x2(p0, p1), pack_bf16x2(p2, p3), pack_bf16x2(p4, p5), pack_bf16x2(p6, p7));

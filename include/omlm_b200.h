@@ -174,11 +174,13 @@ int omlm_ffn_mid_bwd(const void* dhn, const void* hn, const void* u, const float
                      float* dconv_w, int B, int N, int F, int Fp, float drop_p, int act_f16, void* stream);
 
 /* ---- cross entropy (open_musiclm.py:401) --------------------------------------------------------
- * loss_acc[0] += sum of row losses, loss_acc[1] += rows counted; dlogits bf16 [rows, ldd] =
- * (softmax - onehot) * grad_scale, zero in columns [C, Cp). */
-int omlm_cross_entropy(const float* logits, long ld, const int* labels, int label_stride, int rows,
-                       int C, int ignore_index, float grad_scale, void* dlogits_bf16, long ldd,
-                       int Cp, float* loss_acc, void* stream);
+ * loss_acc[0] += loss_scale * sum of row losses, loss_acc[1] += rows counted; dlogits bf16 [rows, ldd] =
+ * (softmax - onehot) * grad_scale, zero in columns [C, Cp).  The label of row r is
+ * labels[(r / rows_per_batch) * batch_stride + (r % rows_per_batch) * label_stride] (rows_per_batch <= 0: one flat
+ * vector, labels[r * label_stride]) -- the strided label view of one quantizer's logit-head group, read in place. */
+int omlm_cross_entropy(const float* logits, long ld, const int* labels, int label_stride, int rows_per_batch,
+                       long batch_stride, int rows, int C, int ignore_index, float grad_scale, float loss_scale,
+                       void* dlogits_bf16, long ldd, int Cp, float* loss_acc, void* stream);
 
 /* ---- optimiser (trainer.py:443-449, optimizer.py:3-34) ------------------------------------------
  * hyper (device, 9 floats): lr, beta1, beta2, eps, wd, 1-beta1^t, 1-beta2^t, max_grad_norm, grad prescale.

@@ -8,11 +8,15 @@ namespace omlm {
 
 constexpr int kCeMaxPerLane = 40;
 
-// loss_acc[0] += sum_rows (lse - logit[label]);  loss_acc[1] += number of non-ignored rows.
+// loss_acc[0] += loss_scale * sum_rows (lse - logit[label]);  loss_acc[1] += number of non-ignored rows.
 // dlogits[row, c] = (softmax(row)[c] - [c == label]) * grad_scale  (bf16, zero for c >= C and ignored rows)
+// The label of row r is labels[(r / rows_per_batch) * batch_stride + (r % rows_per_batch) * label_stride]: the rows of a
+// logit-head group are ordered (sequence b, step t) while its labels sit at positions qi + q t of sequence b's label
+// row -- a strided view, read in place.
 __global__ void __launch_bounds__(256)
 ce_fwd_bwd_kernel(const float* __restrict__ logits, long ld, const int* __restrict__ labels, int label_stride,
-                  int rows, int C, int ignore_index, float grad_scale, __nv_bfloat16* __restrict__ dlogits,
+                  int rows_per_batch, long batch_stride,
+                  int rows, int C, int ignore_index, float grad_scale, float loss_scale, __nv_bfloat16* __restrict__ dlogits,
                   long ldd, int Cp, float* __restrict__ loss_acc) {
   pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -20,7 +24,8 @@ ce_fwd_bwd_kernel(const float* __restrict__ logits, long ld, const int* __restri
   float my_loss = 0.f, my_cnt = 0.f;
   if (row < rows) {
     const float* lr = logits + static_cast<long>(row) * ld;
-    const int label = labels[static_cast<long>(row) * label_stride];
+    const int rb = row / rows_per_batch;
+    const int label = labels[rb * batch_stride + static_cast<long>(row - rb * rows_per_batch) * label_stride];
     float v[kCeMaxPerLane];
     float mx = -INFINITY;
 #pragma unroll
@@ -63,19 +68,20 @@ ce_fwd_bwd_kernel(const float* __restrict__ logits, long ld, const int* __restri
     float a = 0.f, b = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { a += sl[i]; b += sc[i]; }
-    if (b > 0.f) { atomicAdd(&loss_acc[0], a); atomicAdd(&loss_acc[1], b); }
+    if (b > 0.f) { atomicAdd(&loss_acc[0], a * loss_scale); atomicAdd(&loss_acc[1], b); }
   }
 }
 
 }  // namespace omlm
 
-extern "C" int omlm_cross_entropy(const float* logits, long ld, const int* labels, int label_stride, int rows,
-                                  int C, int ignore_index, float grad_scale, void* dlogits_bf16, long ldd,
-                                  int Cp, float* loss_acc, void* stream) {
+extern "C" int omlm_cross_entropy(const float* logits, long ld, const int* labels, int label_stride, int rows_per_batch,
+                                  long batch_stride, int rows, int C, int ignore_index, float grad_scale, float loss_scale,
+                                  void* dlogits_bf16, long ldd, int Cp, float* loss_acc, void* stream) {
   using namespace omlm;
   OMLM_CHECK_ARG(rows > 0 && C > 0 && C <= 32 * kCeMaxPerLane && Cp <= 32 * kCeMaxPerLane, "cross_entropy: unsupported C=%d", C);
+  if (rows_per_batch <= 0) { rows_per_batch = rows; batch_stride = 0; }      // one flat label vector
   OMLM_KLAUNCH((ce_fwd_bwd_kernel), (rows + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream), 
-      logits, ld, labels, label_stride, rows, C, ignore_index, grad_scale,
+      logits, ld, labels, label_stride, rows_per_batch, batch_stride, rows, C, ignore_index, grad_scale, loss_scale,
       reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), ldd, Cp, loss_acc);
   OMLM_LAUNCH_CHECK();
   return 0;

@@ -255,11 +255,14 @@ def gemm_rowstat(a, b, out, hn, gamma, part, *, b_mn=False, M=None, N=None, K=No
     return out
 
 
-def cross_entropy(logits, labels, C, loss_acc, *, grad_scale=0.0, dlogits=None, ignore_index=-100, label_stride=1, rows=None):
+def cross_entropy(logits, labels, C, loss_acc, *, grad_scale=0.0, dlogits=None, ignore_index=-100, label_stride=1, rows=None,
+                  rows_per_batch=0, batch_stride=0, loss_scale=1.0):
+    """labels: int32; flat (rows_per_batch = 0) or the strided view described in include/omlm_b200.h (pass the tensor whose
+    data_ptr is the first label of the group)."""
     rows = logits.shape[0] if rows is None else rows
-    call("omlm_cross_entropy", _p(logits), _L(logits.stride(0)), _p(labels), _I(label_stride), _I(rows), _I(C),
-         _I(ignore_index), _F(grad_scale), _p(dlogits), _L(dlogits.stride(0) if dlogits is not None else 0),
-         _I(dlogits.shape[1] if dlogits is not None else 0), _p(loss_acc), _stream())
+    call("omlm_cross_entropy", _p(logits), _L(logits.stride(0)), _p(labels), _I(label_stride), _I(rows_per_batch), _L(batch_stride),
+         _I(rows), _I(C), _I(ignore_index), _F(grad_scale), _F(loss_scale), _p(dlogits),
+         _L(dlogits.stride(0) if dlogits is not None else 0), _I(dlogits.shape[1] if dlogits is not None else 0), _p(loss_acc), _stream())
 
 
 def grad_sumsq(g, acc, prescale=1.0):

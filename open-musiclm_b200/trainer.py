@@ -66,7 +66,8 @@ class HotPathTrainer:
         # the next step's values while earlier steps are still queued (a pinned buffer would be read late -> wrong step)
         self.hyper_host = torch.zeros(9, dtype=torch.float32)
         self.hyper = torch.zeros(9, dtype=torch.float32, device=eng.dev)
-        self.loss_buf = torch.zeros(grad_accum_every, device=eng.dev)
+        self.loss_acc = torch.zeros(grad_accum_every, 2, device=eng.dev)     # per micro-batch: (weighted loss, rows counted)
+        self.loss_buf = self.loss_acc[:, 0]
         self._mask_draws = 0
         self.use_cuda_graph = use_cuda_graph
         self._graphs = {}
@@ -127,22 +128,21 @@ class HotPathTrainer:
         lab_off = [0]
         for s in range(S):
             lab_off.append(lab_off[-1] + ids[s].shape[1] + 1)
-        loss_parts = []
+        # the CE kernels add  w_s / total_n * (sum of row losses)  straight into this micro-batch's slot of loss_acc and read
+        # their labels through the strided view (sequence b, position qi + q t) of the label plane: no torch op in between
+        acc = self.loss_acc[slot]
+        if slot == 0:
+            self.loss_acc.zero_()
         for s in sorted(weighted):
-            acc = torch.zeros(2, device=dev)
-            lab_s = labels[:, lab_off[s]:lab_off[s + 1]]
             q = eng.seqs[s].num_quantizers
             for gi, (gs, qi, cnt, base) in enumerate(pl.groups):
                 if gs != s:
                     continue
-                # rows ordered (b, t) <-> label (b, qi + q t): strided view of the label plane, made dense per group
-                lab_g = lab_s[:, qi::q].contiguous().view(-1)
                 scale = self.ce_weights[s] / total_n / self.grad_accum_every
-                lib.cross_entropy(ws["logits"][gi], lab_g, eng.C[s], acc, grad_scale=scale,
-                                  dlogits=ws["dlogits"][gi] if backward else None, rows=B * cnt)
-            loss_parts.append(acc[0] * (self.ce_weights[s] / total_n))
-        loss = torch.stack(loss_parts).sum()
-        self.loss_buf[slot] = loss
+                lib.cross_entropy(ws["logits"][gi], labels[0, lab_off[s] + qi:], eng.C[s], acc, grad_scale=scale,
+                                  dlogits=ws["dlogits"][gi] if backward else None, rows=B * cnt, label_stride=q, rows_per_batch=cnt,
+                                  batch_stride=labels.stride(0), loss_scale=self.ce_weights[s] / total_n)
+        loss = acc[0]
         if backward:
             eng.backward_core(pl, ws, src_row, key_mask, weighted, drop, on_ready=reducer.fire if reducer is not None else None)
         return loss

@@ -353,6 +353,16 @@ def test_cross_entropy(lib):
     (ref * 0.37).backward()
     assert rel(dl[:, :C], logits.grad) < 4e-3
     assert float(dl[:, C:].abs().max()) == 0
+    # strided label view of a logit-head group: rows ordered (sequence b, step t), labels at plane[b, off + qi + q t];
+    # the weighted loss goes straight into the accumulator
+    B, cnt, q, qi, off = 9, 37, 3, 1, 5
+    plane = torch.randint(0, C, (B, off + q * cnt + 2), device=DEV, dtype=torch.int32)
+    lg = torch.randn(B * cnt, C, device=DEV) * 4
+    acc2 = torch.zeros(2, device=DEV)
+    lib.cross_entropy(lg, plane[0, off + qi:], C, acc2, rows=B * cnt, label_stride=q, rows_per_batch=cnt, batch_stride=plane.stride(0), loss_scale=0.25)
+    lab = plane[:, off + qi::q][:, :cnt].reshape(-1).long()
+    ref2 = 0.25 * F.cross_entropy(lg, lab, reduction="sum")
+    assert abs(float(acc2[0]) - float(ref2)) / float(ref2) < 1e-5 and float(acc2[1]) == B * cnt
 
 
 def test_adamw_matches_torch(lib):

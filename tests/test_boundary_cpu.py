@@ -94,3 +94,23 @@ def test_pack_job_struct_matches_header():
     assert names == [f[0] for f in lib._PackJob._fields_]
     assert ctypes.sizeof(lib._PackJob) == 3 * 8 + 3 * 8 + 8 * 4
     assert lib._PackJob.unit_start.offset == 40 and lib._PackJob.rows_valid.offset == 48
+
+
+def test_decode_layer_struct_matches_header():
+    """lib._DecodeLayer (ctypes) mirrors `omlm_decode_layer` of include/omlm_b200.h field for field: the per-layer pointer table of
+    the fused decode step is built on the host and read by omlm_decode_step on the device."""
+    import ctypes
+    import re
+    from open_musiclm_b200 import lib
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "omlm_b200.h")).read()
+    end = hdr.index("} omlm_decode_layer;")
+    body = hdr[hdr.rindex("typedef struct {", 0, end) + len("typedef struct {"):end]
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        for part in decl.split(","):
+            names.append(re.sub(r"[\s\*]", " ", part).split()[-1])
+    assert names == [f[0] for f in lib._DecodeLayer._fields_]
+    assert ctypes.sizeof(lib._DecodeLayer) == 13 * 8

@@ -96,6 +96,9 @@ def test_bucket_plan_tiles_the_arena_in_backward_order():
         first = layout[f"transformer.layers.{l}.0.to_q.weight"]
         owner = next(t for t, sl in plan if any(lo <= first < hi for lo, hi in sl))
         assert owner.startswith("layer") and int(owner[5:]) <= l
+    # every slice is a multiple of 64 elements (parameters start on 64-element boundaries, the padding behind the last one
+    # of a span belongs to it): equal parts for any power-of-two world size up to 64 (reduce-scatter mode)
+    assert all((hi - lo) % 64 == 0 for _, sl in plan for lo, hi in sl)
     one = plan_buckets(layout, sizes, total, 5, min_elems=1 << 30)    # everything merged: heads, one layer bucket, tail
     assert [t for t, _ in one] == ["heads", "layer0", "tail"]
 
